@@ -1,0 +1,27 @@
+"""In-tree build of libb200mpc.so with nvcc for sm_100a (B200).  No JIT cache, no pip install: the
+.so lands in dynamic-obstacle-avoidance-mpc_b200/lib/ and travels with the repo snapshot."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+SRC = os.path.join(PKG, "csrc")
+OUT = os.path.join(PKG, "lib", "libb200mpc.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def sources():
+    return [os.path.join(SRC, f) for f in sorted(os.listdir(SRC)) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(os.path.dirname(PKG), "include", "b200mpc.h")]
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    stale = (not os.path.exists(OUT)) or any(os.path.getmtime(s) > os.path.getmtime(OUT) for s in sources())
+    if not (force or stale):
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(SRC, "b200mpc.cu")]
+    subprocess.check_call(cmd)
+    return OUT

@@ -1,0 +1,489 @@
+// b200mpc.cu -- C-ABI of libb200mpc.so (include/b200mpc.h) and the glue kernels around the solve.
+//
+// Host side mirrors the object the reference builds at src/simulation/robot_ocp_problem.py:135-136
+// (AcadosOcpSolver + AcadosSimSolver) for a BATCH of independent problems.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mpc.h"
+#include "mpc_common.cuh"
+#include "mpc_tpp.cuh"
+#ifdef B2MPC_WITH_WPP
+#include "mpc_wpp.cuh"
+#endif
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) return fail(B2MPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct b2mpc {
+    b2mpc_config cfg;
+    int N, M, Bm, nct;
+    int64_t len[B2MPC_N_FIELDS];
+    double* f[B2MPC_N_FIELDS];       // SoA [len][Bm]
+    int32_t* fi[B2MPC_N_IFIELDS];    // [Bm]
+    double* ws;
+    size_t ws_bytes;
+    double* stage_d;                 // device staging for layout conversion (max field len * Bm)
+    double* stage_h;                 // pinned host staging
+    int32_t* stage_hi;
+    size_t stage_elems;
+    int64_t launches;
+    B2Params prm;
+};
+
+extern "C" int b2mpc_abi_version(void) { return B2MPC_ABI_VERSION; }
+extern "C" const char* b2mpc_last_error(void) { return g_err.c_str(); }
+
+extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst, double tf, int32_t max_batch, int32_t device)
+{
+    memset(c, 0, sizeof(*c));
+    c->N = N; c->n_obst = n_obst; c->device = device; c->max_batch = max_batch;
+    c->integrator = 0; c->qp_iter_max = 50; c->lm_scaled_by_dt = 0; c->kernel = 0;   // world_specification.py:48
+    c->pred_corr = 1; c->cond_pred_corr = 1; c->itref_corr_max = 2;
+    c->tf = tf; c->lm = 2.0;                                       // robot_ocp_problem.py:128,132
+    for (int i = 0; i < 4; i++) c->W[i] = 2.0;                     // Q = 2*I4, :26
+    c->W[4] = c->W[5] = 0.15;                                      // R = 0.15*I2, :24
+    for (int i = 0; i < 4; i++) c->W_e[i] = 5.0;                   // Q_e = 5*I4, :27
+    c->lbx[0] = c->lbx[1] = -7.0; c->lbx[2] = c->lbx[3] = -MODEL_WORLD_V_MAX_ROBOT;   // :91
+    c->ubx[0] = c->ubx[1] = 7.0; c->ubx[2] = c->ubx[3] = MODEL_WORLD_V_MAX_ROBOT;     // :92
+    c->lbu[0] = c->lbu[1] = -MODEL_WORLD_C_MAX; c->ubu[0] = c->ubu[1] = MODEL_WORLD_C_MAX;   // :95-96
+    c->r2 = MODEL_R2;                                              // robot_model.py:62
+    c->lh = 0.0; c->uh = 1e5;                                      // :99-103
+    c->zu = 0.0; c->Zu = 0.0;                                      // :118-122
+    c->mu0 = 1e0; c->alpha_min = 1e-8;                             // acados' HPIPM defaults
+    c->res_g_max = 1e-6; c->res_b_max = 1e-8; c->res_d_max = 1e-8; c->res_m_max = 1e-8;
+    c->reg_prim = 1e-15; c->lam_min = 1e-16; c->t_min = 1e-16; c->tau_min = 1e-16; c->thr0 = 1e-1;
+}
+
+static void fill_params(b2mpc* h)
+{
+    const b2mpc_config& c = h->cfg;
+    B2Params& p = h->prm;
+    memset(&p, 0, sizeof(p));
+    p.N = h->N; p.M = h->M; p.Bm = h->Bm; p.B = 0;
+    p.integrator = c.integrator; p.qp_iter_max = c.qp_iter_max;
+    p.pred_corr = c.pred_corr; p.cond_pred_corr = c.cond_pred_corr; p.itref_corr_max = c.itref_corr_max;
+    p.nct = h->nct;
+    p.slots_per_stage = B2Off(h->M).total;
+    p.dt = c.tf / c.N; p.dt2h = 0.5 * p.dt * p.dt;
+    const double lm_s = c.lm_scaled_by_dt ? p.dt * c.lm : c.lm;   // acados-version dependent
+    // v order [u_a,u_alpha,x,y,psi,v,omega]; y order [x,y,v,omega,u_a,u_alpha]; stage cost scaled by dt
+    const double Wv[7] = {c.W[4], c.W[5], c.W[0], c.W[1], 0.0, c.W[2], c.W[3]};
+    const double Wev[7] = {0.0, 0.0, c.W_e[0], c.W_e[1], 0.0, c.W_e[2], c.W_e[3]};
+    for (int i = 0; i < 7; i++) {
+        p.Hd[i] = p.dt * Wv[i] + lm_s; p.Wg[i] = p.dt * Wv[i];
+        p.Hde[i] = i < 2 ? 0.0 : Wev[i] + c.lm; p.Wge[i] = Wev[i];
+    }
+    for (int i = 0; i < 4; i++) { p.lbx[i] = c.lbx[i]; p.ubx[i] = c.ubx[i]; }
+    for (int i = 0; i < 2; i++) { p.lbu[i] = c.lbu[i]; p.ubu[i] = c.ubu[i]; }
+    p.r2 = c.r2; p.lh = c.lh; p.uh = c.uh; p.zu = c.zu; p.Zu = c.Zu;
+    p.mu0 = c.mu0; p.alpha_min = c.alpha_min; p.res_g_max = c.res_g_max; p.res_b_max = c.res_b_max;
+    p.res_d_max = c.res_d_max; p.res_m_max = c.res_m_max; p.reg_prim = c.reg_prim;
+    p.lam_min = c.lam_min; p.t_min = c.t_min; p.tau_min = c.tau_min; p.thr0 = c.thr0;
+    p.X0 = h->f[B2MPC_X0]; p.P = h->f[B2MPC_P]; p.YREF = h->f[B2MPC_YREF]; p.ZL = h->f[B2MPC_ZL]; p.ZZL = h->f[B2MPC_ZZL];
+    p.X = h->f[B2MPC_X]; p.U = h->f[B2MPC_U]; p.SL = h->f[B2MPC_SL]; p.SU = h->f[B2MPC_SU];
+    p.PI = h->f[B2MPC_PI]; p.LAM = h->f[B2MPC_LAM]; p.T = h->f[B2MPC_T]; p.STATS = h->f[B2MPC_STATS];
+    p.STATUS = h->fi[B2MPC_STATUS]; p.QP_ITER = h->fi[B2MPC_QP_ITER]; p.QP_STATUS = h->fi[B2MPC_QP_STATUS];
+    p.WS = h->ws;
+}
+
+extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
+{
+    if (!cfg || !out) return fail(B2MPC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->N < 1 || cfg->N > B2MPC_MAX_N) return fail(B2MPC_EINVAL, "N=%d out of range [1,%d]", cfg->N, B2MPC_MAX_N);
+    if (cfg->n_obst < 1 || cfg->n_obst > B2MPC_MAX_OBST) return fail(B2MPC_EINVAL, "n_obst=%d out of range [1,%d]", cfg->n_obst, B2MPC_MAX_OBST);
+    if (cfg->max_batch < 1) return fail(B2MPC_EINVAL, "max_batch must be >= 1");
+    if (!(cfg->tf > 0.0)) return fail(B2MPC_EINVAL, "tf must be > 0");
+    if (cfg->integrator != 0 && cfg->integrator != 1) return fail(B2MPC_EINVAL, "integrator must be 0 (IRK-GL4) or 1 (RK4)");
+    if (cfg->qp_iter_max < 1) return fail(B2MPC_EINVAL, "qp_iter_max must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(B2MPC_ENODEV, "no CUDA device: libb200mpc has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(B2MPC_ENODEV, "device %d not present (%d devices)", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    b2mpc* h = new b2mpc();
+    memset((void*)h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->N = cfg->N; h->M = cfg->n_obst; h->Bm = cfg->max_batch; h->nct = 12 + 4 * cfg->n_obst;
+    const int N = h->N, M = h->M;
+    h->len[B2MPC_X0] = 5; h->len[B2MPC_P] = (int64_t)(N + 1) * 2 * M; h->len[B2MPC_YREF] = (int64_t)(N + 1) * 6;
+    h->len[B2MPC_ZL] = h->len[B2MPC_ZZL] = h->len[B2MPC_SL] = h->len[B2MPC_SU] = (int64_t)(N + 1) * M;
+    h->len[B2MPC_X] = (int64_t)(N + 1) * 5; h->len[B2MPC_U] = (int64_t)N * 2; h->len[B2MPC_PI] = (int64_t)N * 5;
+    h->len[B2MPC_LAM] = h->len[B2MPC_T] = (int64_t)(N + 1) * h->nct;
+    h->len[B2MPC_STATS] = 8; h->len[B2MPC_GOAL] = 2; h->len[B2MPC_OBST] = (int64_t)M * 4;
+    int64_t maxlen = 0;
+    for (int i = 0; i < B2MPC_N_FIELDS; i++) {
+        if (h->len[i] > maxlen) maxlen = h->len[i];
+        size_t bytes = sizeof(double) * (size_t)h->len[i] * h->Bm;
+        if (cudaMalloc(&h->f[i], bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(field %d, %zu B) failed", i, bytes); }
+        cudaMemset(h->f[i], 0, bytes);
+    }
+    for (int i = 0; i < B2MPC_N_IFIELDS; i++) {
+        if (cudaMalloc(&h->fi[i], sizeof(int32_t) * h->Bm) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(int field) failed"); }
+        cudaMemset(h->fi[i], 0, sizeof(int32_t) * h->Bm);
+    }
+    h->ws_bytes = sizeof(double) * (size_t)B2Off(M).total * (N + 1) * h->Bm;
+    if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(workspace, %zu B) failed", h->ws_bytes); }
+    cudaMemset(h->ws, 0, h->ws_bytes);
+    h->stage_elems = (size_t)maxlen * h->Bm;
+    if (cudaMalloc(&h->stage_d, sizeof(double) * h->stage_elems) != cudaSuccess ||
+        cudaMallocHost(&h->stage_h, sizeof(double) * h->stage_elems) != cudaSuccess ||
+        cudaMallocHost(&h->stage_hi, sizeof(int32_t) * h->Bm) != cudaSuccess) {
+        b2mpc_destroy(h);
+        return fail(B2MPC_ENOMEM, "staging allocation failed");
+    }
+    fill_params(h);
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return B2MPC_OK;
+}
+
+extern "C" int b2mpc_destroy(b2mpc* h)
+{
+    if (!h) return B2MPC_OK;
+    cudaSetDevice(h->cfg.device);
+    for (int i = 0; i < B2MPC_N_FIELDS; i++) if (h->f[i]) cudaFree(h->f[i]);
+    for (int i = 0; i < B2MPC_N_IFIELDS; i++) if (h->fi[i]) cudaFree(h->fi[i]);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stage_d) cudaFree(h->stage_d);
+    if (h->stage_h) cudaFreeHost(h->stage_h);
+    if (h->stage_hi) cudaFreeHost(h->stage_hi);
+    delete h;
+    return B2MPC_OK;
+}
+
+extern "C" int64_t b2mpc_field_len(const b2mpc* h, int field)
+{
+    if (!h || field < 0 || field >= B2MPC_N_FIELDS) return -1;
+    return h->len[field];
+}
+extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)h->ws_bytes : -1; }
+extern "C" int64_t b2mpc_launch_count(const b2mpc* h) { return h ? h->launches : -1; }
+extern "C" double* b2mpc_field_ptr(b2mpc* h, int field)
+{
+    if (!h || field < 0 || field >= B2MPC_N_FIELDS) return nullptr;
+    return h->f[field];
+}
+
+// ------------------------------------------------------------------ layout conversion kernels
+// dst[len][Bm] (SoA) <- src[batch][len] (AoS), tiled through shared memory so both sides coalesce
+__global__ void b2_aos_to_soa(const double* __restrict__ src, double* __restrict__ dst, int len, int batch, int Bm)
+{
+    __shared__ double tile[32][33];
+    const int b0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int b = b0 + r, l = l0 + threadIdx.x;
+        if (b < batch && l < len) tile[r][threadIdx.x] = src[(size_t)b * len + l];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int l = l0 + r, b = b0 + threadIdx.x;
+        if (b < batch && l < len) dst[(size_t)l * Bm + b] = tile[threadIdx.x][r];
+    }
+}
+__global__ void b2_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int len, int batch, int Bm)
+{
+    __shared__ double tile[32][33];
+    const int b0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int l = l0 + r, b = b0 + threadIdx.x;
+        if (b < batch && l < len) tile[r][threadIdx.x] = src[(size_t)l * Bm + b];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int b = b0 + r, l = l0 + threadIdx.x;
+        if (b < batch && l < len) dst[(size_t)b * len + l] = tile[threadIdx.x][r];
+    }
+}
+
+static int check_batch(const b2mpc* h, int64_t batch)
+{
+    if (!h) return fail(B2MPC_EINVAL, "null handle");
+    if (batch < 1 || batch > h->Bm) return fail(B2MPC_EBATCH, "batch %lld out of range [1,%d]", (long long)batch, h->Bm);
+    return B2MPC_OK;
+}
+
+extern "C" int b2mpc_set(b2mpc* h, int field, const double* dptr, int64_t batch, int layout, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (field < 0 || field >= B2MPC_N_FIELDS || !dptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int len = (int)h->len[field];
+    if (layout == B2MPC_LAYOUT_SOA) {
+        CUDA_TRY(cudaMemcpy2DAsync(h->f[field], sizeof(double) * h->Bm, dptr, sizeof(double) * batch,
+                                   sizeof(double) * batch, len, cudaMemcpyDeviceToDevice, st));
+    } else if (layout == B2MPC_LAYOUT_AOS) {
+        dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((len + 31) / 32)), block(32, 8);
+        b2_aos_to_soa<<<grid, block, 0, st>>>(dptr, h->f[field], len, (int)batch, h->Bm);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else return fail(B2MPC_EINVAL, "bad layout %d", layout);
+    return B2MPC_OK;
+}
+
+extern "C" int b2mpc_get(b2mpc* h, int field, double* dptr, int64_t batch, int layout, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (field < 0 || field >= B2MPC_N_FIELDS || !dptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int len = (int)h->len[field];
+    if (layout == B2MPC_LAYOUT_SOA) {
+        CUDA_TRY(cudaMemcpy2DAsync(dptr, sizeof(double) * batch, h->f[field], sizeof(double) * h->Bm,
+                                   sizeof(double) * batch, len, cudaMemcpyDeviceToDevice, st));
+    } else if (layout == B2MPC_LAYOUT_AOS) {
+        dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((len + 31) / 32)), block(32, 8);
+        b2_soa_to_aos<<<grid, block, 0, st>>>(h->f[field], dptr, len, (int)batch, h->Bm);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else return fail(B2MPC_EINVAL, "bad layout %d", layout);
+    return B2MPC_OK;
+}
+
+extern "C" int b2mpc_get_i32(b2mpc* h, int ifield, int32_t* dptr, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (ifield < 0 || ifield >= B2MPC_N_IFIELDS || !dptr) return fail(B2MPC_EINVAL, "bad int field %d or null pointer", ifield);
+    CUDA_TRY(cudaMemcpyAsync(dptr, h->fi[ifield], sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2MPC_OK;
+}
+
+// host variants: batch-first host memory <-> SoA device fields through the device staging buffer.
+// The async H2D from pageable memory is staged by the driver; pass pinned memory for full overlap.
+extern "C" int b2mpc_set_host(b2mpc* h, int field, const double* hptr, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (field < 0 || field >= B2MPC_N_FIELDS || !hptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->len[field] * batch;
+    CUDA_TRY(cudaMemcpyAsync(h->stage_d, hptr, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    return b2mpc_set(h, field, h->stage_d, batch, B2MPC_LAYOUT_AOS, stream);
+}
+extern "C" int b2mpc_get_host(b2mpc* h, int field, double* hptr, int64_t batch, void* stream)
+{
+    int rc = b2mpc_get(h, field, h ? h->stage_d : nullptr, batch, B2MPC_LAYOUT_AOS, stream);
+    if (rc) return rc;
+    if (!hptr) return fail(B2MPC_EINVAL, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->len[field] * batch;
+    CUDA_TRY(cudaMemcpyAsync(hptr, h->stage_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_get_i32_host(b2mpc* h, int ifield, int32_t* hptr, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (ifield < 0 || ifield >= B2MPC_N_IFIELDS || !hptr) return fail(B2MPC_EINVAL, "bad int field %d or null pointer", ifield);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(hptr, h->fi[ifield], sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B2MPC_OK;
+}
+
+// ------------------------------------------------------------------ glue kernels
+// parameterize_slack(), robot_ocp_problem.py:145-152
+__global__ void b2_prepare_slack(const double* __restrict__ X0, const double* __restrict__ GOAL, double* __restrict__ ZL,
+                                 double* __restrict__ ZZL, int N, int M, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double d0 = X0[0 * (size_t)Bm + b] - GOAL[0 * (size_t)Bm + b], d1 = X0[1 * (size_t)Bm + b] - GOAL[1 * (size_t)Bm + b];
+    const double v = X0[3 * (size_t)Bm + b], w = X0[4 * (size_t)Bm + b];
+    const double scale = 1e4 * (d0 * d0 + d1 * d1 + v * v + w * w + 50.0);
+    for (int i = 0; i <= N; i++) {
+        const double a = scale * (N - i) / N;
+        for (int j = 0; j < M; j++) {
+            ZL[((size_t)i * M + j) * Bm + b] = a;
+            ZZL[((size_t)i * M + j) * Bm + b] = a;
+        }
+    }
+}
+// ocp_solver.reset() + set_initial_guess(), robot_ocp_problem.py:286-306 (incl. aliasing quirk :301-302)
+__global__ void b2_reset(double* __restrict__ X0, double* __restrict__ X, double* __restrict__ U, double* __restrict__ SL,
+                         double* __restrict__ SU, const uint8_t* __restrict__ mask, int N, int M, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (mask && !mask[b]) return;
+    X0[3 * (size_t)Bm + b] = 0.0; X0[4 * (size_t)Bm + b] = 0.0;
+    double x0[5];
+    for (int i = 0; i < 5; i++) x0[i] = X0[i * (size_t)Bm + b];
+    for (int k = 0; k <= N; k++) {
+        for (int i = 0; i < 5; i++) X[((size_t)k * 5 + i) * Bm + b] = x0[i];
+        if (k < N) { U[((size_t)k * 2) * Bm + b] = 0.0; U[((size_t)k * 2 + 1) * Bm + b] = 0.0; }
+        for (int j = 0; j < M; j++) { SL[((size_t)k * M + j) * Bm + b] = 0.0; SU[((size_t)k * M + j) * Bm + b] = 0.0; }
+    }
+}
+// ocp_integrator: X0 <- F(X0, U[0]), robot_ocp_problem.py:207-212 (same IRK as the OCP, :136)
+__global__ void b2_sim(double* __restrict__ X0, const double* __restrict__ U, double dt, int integrator, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double x[5], u[2], xn[5], sv[10];
+    for (int i = 0; i < 5; i++) x[i] = X0[i * (size_t)Bm + b];
+    u[0] = U[b]; u[1] = U[(size_t)Bm + b];
+    if (integrator == 1) model_rk4_step(x, u, dt, xn, sv); else model_gl4_step(x, u, dt, xn, sv);
+    for (int i = 0; i < 5; i++) X0[i * (size_t)Bm + b] = xn[i];
+}
+// warm-start shift, robot_ocp_problem.py:253-258
+__global__ void b2_shift(double* __restrict__ X, double* __restrict__ U, int N, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int j = 0; j < N - 1; j++) {
+        for (int i = 0; i < 5; i++) X[((size_t)j * 5 + i) * Bm + b] = X[((size_t)(j + 1) * 5 + i) * Bm + b];
+        for (int i = 0; i < 2; i++) U[((size_t)j * 2 + i) * Bm + b] = U[((size_t)(j + 1) * 2 + i) * Bm + b];
+    }
+    for (int i = 0; i < 5; i++) X[((size_t)(N - 1) * 5 + i) * Bm + b] = X[((size_t)N * 5 + i) * Bm + b];
+    U[((size_t)(N - 1) * 2) * Bm + b] = 0.0; U[((size_t)(N - 1) * 2 + 1) * Bm + b] = 0.0;
+}
+
+extern "C" int b2mpc_prepare_slack(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    b2_prepare_slack<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->f[B2MPC_X0], h->f[B2MPC_GOAL], h->f[B2MPC_ZL], h->f[B2MPC_ZZL], h->N, h->M, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_reset(b2mpc* h, const uint8_t* dmask, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    b2_reset<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->f[B2MPC_X0], h->f[B2MPC_X], h->f[B2MPC_U], h->f[B2MPC_SL], h->f[B2MPC_SU], dmask, h->N, h->M, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_sim(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    b2_sim<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->f[B2MPC_X0], h->f[B2MPC_U], h->prm.dt, h->cfg.integrator, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_shift(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    b2_shift<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->f[B2MPC_X], h->f[B2MPC_U], h->N, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+
+// ------------------------------------------------------------------ the solve
+extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2Params p = h->prm;
+    p.B = (int)batch;
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
+    switch (h->M) {
+        case 5: b2_rti_solve_tpp<5><<<blocks, threads, 0, st>>>(p); break;
+        default: b2_rti_solve_tpp<0><<<blocks, threads, 0, st>>>(p); break;
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+
+extern "C" int b2mpc_solve_host(b2mpc* h, int64_t batch, const double* x0, const double* p, const double* yref,
+                                const double* zl, const double* Zl, double* x, double* u, double* sl, double* su,
+                                int32_t* status, int32_t* qp_iter, void* stream)
+{
+    int rc;
+    if (!x0 || !p || !yref || !zl || !Zl || !x || !u || !sl || !su) return fail(B2MPC_EINVAL, "null pointer");
+    if ((rc = b2mpc_set_host(h, B2MPC_X0, x0, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_P, p, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_YREF, yref, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_ZL, zl, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_ZZL, Zl, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_X, x, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_U, u, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_SL, sl, batch, stream))) return rc;
+    if ((rc = b2mpc_set_host(h, B2MPC_SU, su, batch, stream))) return rc;
+    if ((rc = b2mpc_solve(h, batch, stream))) return rc;
+    if ((rc = b2mpc_get_host(h, B2MPC_X, x, batch, stream))) return rc;
+    if ((rc = b2mpc_get_host(h, B2MPC_U, u, batch, stream))) return rc;
+    if ((rc = b2mpc_get_host(h, B2MPC_SL, sl, batch, stream))) return rc;
+    if ((rc = b2mpc_get_host(h, B2MPC_SU, su, batch, stream))) return rc;
+    if (status && (rc = b2mpc_get_i32_host(h, B2MPC_STATUS, status, batch, stream))) return rc;
+    if (qp_iter && (rc = b2mpc_get_i32_host(h, B2MPC_QP_ITER, qp_iter, batch, stream))) return rc;
+    return B2MPC_OK;
+}
+
+// ------------------------------------------------------------------ FP64 pipe microbenchmark
+__global__ void b2_dfma_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int b2mpc_dfma_peak(int device, double* tflops_out)
+{
+    if (!tflops_out) return fail(B2MPC_EINVAL, "null pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B2MPC_ENODEV, "no such CUDA device %d", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        b2_dfma_kernel<<<blocks, threads>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops_out = best;
+    return B2MPC_OK;
+}

@@ -1,0 +1,143 @@
+/*
+ * b200mpc.h -- C-ABI of libb200mpc.so: batched FP64 SQP-RTI nonlinear MPC on B200 (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of abdelhakim96/Dynamic-Obstacle-Avoidance-MPC: the
+ * acados solver object driven from src/simulation/robot_ocp_problem.py.  Each entry point
+ * names the reference call it replaces (file:line, relative to the reference repo); the
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * dynamic-obstacle-avoidance-mpc_b200/b200mpc/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  `stream` is a cudaStream_t passed as void*
+ *     (e.g. torch.cuda.current_stream().cuda_stream); 0 = legacy default stream.
+ *   - device arrays are FP64, contiguous, "batch-last" structure-of-arrays: field[len][batch]
+ *     (B2MPC_LAYOUT_SOA), or batch-first field[batch][len] (B2MPC_LAYOUT_AOS, transposed on
+ *     device).  Host variants (`*_host`) take batch-first host memory (what numpy users hold)
+ *     and do the H2D/D2H copies on `stream` through the handle's pinned staging buffers.
+ *   - the handle owns all device memory (sized by max_batch at create; no allocation later);
+ *     callers own what they pass; pointers are borrowed for the stream-ordered call only.
+ *   - every function returns 0 on success or a negative B2MPC_E* code, message via
+ *     b2mpc_last_error().  Per-problem numerical status uses acados codes (0 ok, 4 QP failure).
+ *   - a handle is not thread-safe; no call synchronises the stream unless documented.
+ *   - there is NO CPU fallback: without a CUDA device b2mpc_create fails.
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2MPC_ABI_VERSION 1
+#define B2MPC_MAX_OBST 32
+#define B2MPC_MAX_N 128
+
+typedef struct b2mpc b2mpc;   /* opaque; one per (device, max_batch, dims) */
+
+/* Everything robot_ocp_problem.py:54-132 + world_specification.py:7-48 freeze when the
+ * reference constructs AcadosOcpSolver (:135), plus acados' HPIPM option block. */
+typedef struct b2mpc_config {
+    int32_t N;               /* ocp.dims.N = N_SOLV, robot_ocp_problem.py:57 */
+    int32_t n_obst;          /* N_OBST, world_specification.py:25; 1..B2MPC_MAX_OBST */
+    int32_t device;          /* CUDA ordinal */
+    int32_t max_batch;       /* independent problems per solve */
+    int32_t integrator;      /* 0 = IRK Gauss-Legendre-4 (reference, :129), 1 = RK4 */
+    int32_t qp_iter_max;     /* solver_options.qp_solver_iter_max, :131 */
+    int32_t lm_scaled_by_dt; /* acados-version switch for levenberg_marquardt scaling */
+    int32_t kernel;          /* 0 = auto, 1 = thread-per-problem, 2 = warp-per-problem */
+    int32_t pred_corr, cond_pred_corr, itref_corr_max, reserved;
+    double tf;               /* solver_options.tf, :132 */
+    double lm;               /* solver_options.levenberg_marquardt, :128 */
+    double W[6];             /* diag(cost.W) over y=[x,y,v,omega,u_a,u_alpha], :78-80 */
+    double W_e[4];           /* diag(cost.W_e) over [x,y,v,omega], :83 */
+    double lbx[4], ubx[4];   /* constraints.lbx/ubx on idxbx={0,1,3,4}, :91-93 */
+    double lbu[2], ubu[2];   /* constraints.lbu/ubu, :95-97 */
+    double r2;               /* (R_OBST+R_ROBOT+MARGIN)^2 inside con_h_expr, robot_model.py:62 */
+    double lh, uh;           /* constraints.lh/uh (= lh_e/uh_e), :99-103 */
+    double zu, Zu;           /* cost.zu/Zu (upper-side slack penalty), :118-122 */
+    double mu0, alpha_min, res_g_max, res_b_max, res_d_max, res_m_max;   /* HPIPM */
+    double reg_prim, lam_min, t_min, tau_min, thr0;                      /* HPIPM */
+} b2mpc_config;
+
+/* fields of b2mpc_set / b2mpc_get; len = doubles per problem */
+enum {
+    B2MPC_X0 = 0,     /* [5]            set(0,'lbx'/'ubx',x0), :191-192                     */
+    B2MPC_P = 1,      /* [(N+1)*2M]     set(i,'p',P[i]) / set_params_sparse, :164-166        */
+    B2MPC_YREF = 2,   /* [(N+1)*6]      cost_set(i,'yref',..), :70,77,284 (node N: first 4)  */
+    B2MPC_ZL = 3,     /* [(N+1)*M]      cost_set(i,'zl',..), :151                            */
+    B2MPC_ZZL = 4,    /* [(N+1)*M]      cost_set(i,'Zl',..), :152                            */
+    B2MPC_X = 5,      /* [(N+1)*5]      set/get(i,'x'), :232,254,257,306                     */
+    B2MPC_U = 6,      /* [N*2]          set/get(i,'u'), :140,198,255,258,305                 */
+    B2MPC_SL = 7,     /* [(N+1)*M]      get(i,'sl') (lower slack iterate; reset() zeroes)    */
+    B2MPC_SU = 8,     /* [(N+1)*M]      get(i,'su')                                          */
+    B2MPC_PI = 9,     /* [N*5]          get(i,'pi')  (output only)                           */
+    B2MPC_LAM = 10,   /* [(N+1)*(12+4M)] get(i,'lam') padded [lb6 lg ub6 ug ls us] (output)  */
+    B2MPC_T = 11,     /* [(N+1)*(12+4M)] get(i,'t')   (output)                               */
+    B2MPC_STATS = 12, /* [8] res_g,res_b,res_d,res_m,mu,alpha,n_itref,0 at exit (output)     */
+    B2MPC_GOAL = 13,  /* [2]            sub-goal used by b2mpc_prepare_slack / closed loop   */
+    B2MPC_OBST = 14,  /* [M*4]          obstacle states (x,y,vx,vy), visualization.py:10-18  */
+    B2MPC_N_FIELDS = 15
+};
+enum { B2MPC_STATUS = 0, B2MPC_QP_ITER = 1, B2MPC_QP_STATUS = 2, B2MPC_N_IFIELDS = 3 };
+enum { B2MPC_LAYOUT_SOA = 0, B2MPC_LAYOUT_AOS = 1 };
+
+enum {
+    B2MPC_OK = 0, B2MPC_EINVAL = -1, B2MPC_ENODEV = -2, B2MPC_ENOMEM = -3,
+    B2MPC_ECUDA = -4, B2MPC_EBATCH = -5
+};
+
+int b2mpc_abi_version(void);
+const char *b2mpc_last_error(void);                              /* thread-local */
+
+/* reference defaults: world_specification.py + robot_ocp_problem.py:24-27,91-132 */
+void b2mpc_default_config(b2mpc_config *cfg, int32_t N, int32_t n_obst, double tf,
+                          int32_t max_batch, int32_t device);
+
+/* AcadosOcpSolver(ocp, json_file=...) + AcadosSimSolver(...), robot_ocp_problem.py:135-136 */
+int b2mpc_create(const b2mpc_config *cfg, b2mpc **out);
+int b2mpc_destroy(b2mpc *h);                                     /* solver teardown */
+int64_t b2mpc_field_len(const b2mpc *h, int field);              /* doubles per problem */
+int64_t b2mpc_workspace_bytes(const b2mpc *h);
+
+/* ocp_solver.set / cost_set / set_params_sparse (:151-152,:164-166,:191-192,:254-258,:305-306) */
+int b2mpc_set(b2mpc *h, int field, const double *dptr, int64_t batch, int layout, void *stream);
+/* ocp_solver.get(i, 'u'/'x') (:198,:232,:240) and multipliers/statistics */
+int b2mpc_get(b2mpc *h, int field, double *dptr, int64_t batch, int layout, void *stream);
+int b2mpc_get_i32(b2mpc *h, int ifield, int32_t *dptr, int64_t batch, void *stream);
+/* same, host memory, batch-first; H2D/D2H on `stream`; get_* synchronise the stream */
+int b2mpc_set_host(b2mpc *h, int field, const double *hptr, int64_t batch, void *stream);
+int b2mpc_get_host(b2mpc *h, int field, double *hptr, int64_t batch, void *stream);
+int b2mpc_get_i32_host(b2mpc *h, int ifield, int32_t *hptr, int64_t batch, void *stream);
+/* raw device pointer of a handle-owned field (SoA, row stride = max_batch) for zero-copy views */
+double *b2mpc_field_ptr(b2mpc *h, int field);
+
+/* parameterize_slack(), robot_ocp_problem.py:145-152: ZL,ZZL <- f(X0, GOAL) on device */
+int b2mpc_prepare_slack(b2mpc *h, int64_t batch, void *stream);
+/* ocp_solver.reset() + set_initial_guess(), :286-306 (mask: uint8 per problem, NULL = all);
+ * like the reference it zeroes v,omega of X0 itself (aliasing quirk :301-302) */
+int b2mpc_reset(b2mpc *h, const uint8_t *dmask, int64_t batch, void *stream);
+/* ocp_solver.solve(), :195 -- one SQP_RTI iteration for every problem; fills STATUS, QP_ITER */
+int b2mpc_solve(b2mpc *h, int64_t batch, void *stream);
+/* ocp_integrator.set/solve/get, :207-212: X0 <- F(X0, U[0]) */
+int b2mpc_sim(b2mpc *h, int64_t batch, void *stream);
+/* warm-start shift, :253-258 */
+int b2mpc_shift(b2mpc *h, int64_t batch, void *stream);
+/* number of kernels launched by this handle so far (for bench accounting) */
+int64_t b2mpc_launch_count(const b2mpc *h);
+
+/* whole call a user of the reference makes per control step, on HOST batch-first buffers:
+ * set x0/p/yref/zl/Zl + warm iterate (x,u,sl,su) -> solve -> read back iterate, status, qp_iter.
+ * Synchronises `stream` before returning. */
+int b2mpc_solve_host(b2mpc *h, int64_t batch, const double *x0, const double *p, const double *yref,
+                     const double *zl, const double *Zl, double *x, double *u, double *sl, double *su,
+                     int32_t *status, int32_t *qp_iter, void *stream);
+
+/* FP64 FMA-pipe microbenchmark (register-resident DFMA chains) -> achieved TFLOP/s; the
+ * roofline denominator bench.py quotes, since MEASURED_PEAKS.json has no FP64 entry */
+int b2mpc_dfma_peak(int device, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
