@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""bench.py -- MPC solves/sec of the batched SQP-RTI hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (CUDA)
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm (oracle port, all host cores)
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU, env-sharded
+
+A "step" is ONE SQP-RTI solve (robot_ocp_problem.py:195) of a batch of independent synthetic
+scenarios (4096 random start/obstacle scenarios, N=20, Tf=2 s, 5 moving
+obstacles) per GPU.  Every step starts from the same cold iterate (set_initial_guess state), so
+every step does identical work; the iterate is restored from a pristine device copy and L2 is
+flushed between steps, both outside the per-step CUDA-event pairs.
+
+Prints one JSON line (rank 0).  See README / DESIGN.md for the field definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dynamic-obstacle-avoidance-mpc_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "MPC solves/sec (SQP-RTI, N=20, Tf=2 s, 5 obstacles)"
+UNIT = "solves/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=4096)
+    ap.add_argument("--N", type=int, default=20)
+    ap.add_argument("--n-obst", type=int, default=5)
+    ap.add_argument("--tf", type=float, default=2.0)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 thread-per-problem, 2 warp-per-problem")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"batched SQP-RTI, {a.batch_per_gpu} random start/obstacle scenarios per GPU, N={a.N}, "
+            f"Tf={a.tf:g} s, {a.n_obst} moving obstacles, cold start (set_initial_guess iterate)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_arm(a, sample, nthreads, reps=1):
+    """times the oracle port on `sample` problems of the same workload with `nthreads` host threads"""
+    from b200mpc import world
+    from oracle import pyoracle as po
+    dims = world.MpcDims(a.N, a.n_obst, a.tf)
+    sc = world.random_scenarios(sample, dims, seed=a.seed)
+    cfg = po.default_config(a.N, a.n_obst, a.tf)
+    best = None
+    for _ in range(reps):
+        x, u, sl, su = (sc[k].copy() for k in ("x", "u", "sl", "su"))
+        t0 = time.perf_counter()
+        st, it, _ = po.rti_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], x, u, sl, su, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample / best, best, float(it.mean())
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU algorithm (oracle port; acados itself is not installable
+    offline -- parity unpinned) on all host cores; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = a.cpu_sample or min(a.batch_per_gpu, 4096)
+    for _ in range(a.warmup):
+        cpu_arm(a, min(sample, 256), cores)
+    times = []
+    for _ in range(a.steps):
+        v, dt, mean_it = cpu_arm(a, sample, cores)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} problems of the same workload per step, pthreads over problems, "
+                                   "oracle/mpc_oracle.c (CPU restatement of the acados algorithm -- not acados)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_qp_iter": mean_it,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    from b200mpc import BatchedMpcSolver, dfma_peak_tflops, flops, world
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = a.batch_per_gpu
+    dims = world.MpcDims(a.N, a.n_obst, a.tf)
+    # env-sharded: rank r owns scenarios [r*B, (r+1)*B) of the global seeded set (no cross-GPU traffic)
+    sc = world.random_scenarios(B, dims, seed=a.seed + 1000 * rank)
+    solver = BatchedMpcSolver(a.N, a.n_obst, a.tf, max_batch=B, device=local_rank, kernel=a.kernel)
+    names_in = ("x0", "p", "yref", "zl", "Zl")
+    names_it = ("x", "u", "sl", "su")
+    dev_t = {k: torch.from_numpy(sc[k]).to(dev) for k in names_in + names_it}
+    for k in names_in:
+        solver.set(k, dev_t[k])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def restore():
+        for k in names_it:
+            solver.set(k, dev_t[k])
+
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        restore(); flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        solver.solve(B)
+        e1.record(stream)
+        return e0, e1
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize(dev)
+    peak_tf = dfma_peak_tflops(local_rank)
+
+    # ---------------- timed region: device-resident inputs ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = solver.launch_count
+    evs = [step_device() for _ in range(a.steps)]
+    torch.cuda.synchronize(dev)
+    if world_size > 1:
+        dist.barrier()
+    l1 = solver.launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = float(np.sum(step_ms))
+    qp_iter = solver.get_int("qp_iter", B).cpu().numpy()
+    status = solver.get_int("status", B).cpu().numpy()
+    # restore()'s 4 layout kernels per step are not the solve; count the solve launches only
+    gpu_launches = (l1 - l0) - 4 * a.steps
+
+    # ---------------- e2e: host buffers through the public API ----------------
+    host = {k: torch.from_numpy(sc[k]).pin_memory().numpy() for k in names_in}
+    host_it0 = {k: sc[k].copy() for k in names_it}
+    host_it = {k: torch.from_numpy(sc[k].copy()).pin_memory().numpy() for k in names_it}
+
+    def step_host():
+        for k in names_it:
+            np.copyto(host_it[k], host_it0[k])
+        t0 = time.perf_counter()
+        st, it = solver.solve_host(host["x0"], host["p"], host["yref"], host["zl"], host["Zl"],
+                                   host_it["x"], host_it["u"], host_it["sl"], host_it["su"])
+        return time.perf_counter() - t0
+
+    for _ in range(2):
+        step_host()
+    if world_size > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(a.steps, 10))
+    e2e_s = float(np.sum([step_host() for _ in range(e2e_steps)]))
+    h2d = sum(host[k].nbytes for k in names_in) + sum(host_it[k].nbytes for k in names_it)
+    d2h = sum(host_it[k].nbytes for k in names_it) + 2 * 4 * B
+    # device result of the host path equals the device path
+    assert np.array_equal(host_it["u"], solver.get("u", B).cpu().numpy())
+
+    # ---------------- reduce over ranks (max time; sum of work) ----------------
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    s = torch.tensor([float(B), float(qp_iter.sum()), float((status != 0).sum())], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_s_max = t.tolist()
+    tot_B, tot_it, tot_fail = s.tolist()
+
+    if rank == 0:
+        ms_per_step = total_ms_max / a.steps
+        value = tot_B * a.steps / (total_ms_max * 1e-3)
+        e2e_value = tot_B * e2e_steps / e2e_s_max
+        mean_it = tot_it / tot_B
+        fl = flops.flops_per_solve(a.N, a.n_obst, mean_it) * B            # per launch (per GPU)
+        kern_s = (float(np.mean(step_ms)) * 1e-3)
+        achieved_tf = fl / kern_s / 1e12
+        cnt = flops.counts(a.N, a.n_obst)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "global_batch": int(tot_B), "l2": "flushed between steps (256 MiB memset)",
+                       "kernel": "thread-per-problem" if a.kernel in (0, 1) else "warp-per-problem",
+                       "parallelism": f"env-sharded x{world_size}, no data-path collective"},
+            "p50_latency_ms_per_batch": float(np.median(step_ms)),
+            "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "self-measured register-resident DFMA chains (b2mpc_dfma_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 ~37-40 TFLOP/s",
+                         "flops_per_launch": fl, "kernel_ms": kern_s * 1e3,
+                         "hbm": {"achieved": B * cnt["bytes"] / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": B * cnt["bytes"] / kern_s / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "BatchedMpcSolver.solve_host -> b2mpc_solve_host (pinned host buffers)"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+        }
+        if not a.no_cpu_baseline and world_size == 1:
+            cores = os.cpu_count() or 1
+            sample = a.cpu_sample or 4096
+            v, dt, cit = cpu_arm(a, sample, cores)
+            reps = 1
+            while dt * reps < 8.0 and reps < 64:       # ~10 s of CPU work in total
+                v2, dt2, _ = cpu_arm(a, sample, cores)
+                v = max(v, v2); reps += 1
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} problems of the same workload x {reps} repetitions (best), "
+                                              "pthreads over problems; oracle/mpc_oracle.c = CPU restatement of the acados "
+                                              "algorithm, not acados (parity unpinned)"}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

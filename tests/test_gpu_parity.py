@@ -73,7 +73,8 @@ def test_rti_solve_matches_oracle(torch_cuda, oracle, N, M, tf, B):
     out, ref = _solve_both(torch_cuda, oracle, dims, sc, B)
     conv = _check_parity(out, ref)
     assert conv.mean() > 0.5
-    assert _rel_rows(out["sl"], ref["sl"])[conv].max() < 1e-5 and _rel_rows(out["su"], ref["su"])[conv].max() < 1e-5
+    # slack iterates are weakly determined (zero cost on the upper side / at the terminal node)
+    assert _rel_rows(out["sl"], ref["sl"])[conv].max() < 1e-4 and _rel_rows(out["su"], ref["su"])[conv].max() < 1e-4
     # exit residuals below the HPIPM tolerances for converged problems (KKT residual bar)
     assert (out["stats"][conv, 0] <= 1e-6).all() and (out["stats"][conv, 1] <= 1e-8).all()
     assert (out["stats"][conv, 2] <= 1e-8).all() and (out["stats"][conv, 3] <= 1e-8).all()
