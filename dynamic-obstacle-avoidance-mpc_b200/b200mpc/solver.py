@@ -25,9 +25,9 @@ class BatchedMpcSolver:
         self.torch = torch
         self.cfg = capi.default_config(N, n_obst, tf, max_batch, device, **overrides)
         self.N, self.M, self.tf, self.max_batch, self.device = N, n_obst, tf, max_batch, device
-        self.dt = tf / N
         self._h = C.c_void_p()
         capi.check(capi.lib().b2mpc_create(C.byref(self.cfg), C.byref(self._h)))
+        self.dt = tf / N
         self._shapes = {
             capi.X0: (5,), capi.P: (N + 1, 2 * n_obst), capi.YREF: (N + 1, 6), capi.ZL: (N + 1, n_obst),
             capi.ZZL: (N + 1, n_obst), capi.X: (N + 1, 5), capi.U: (N, 2), capi.SL: (N + 1, n_obst),

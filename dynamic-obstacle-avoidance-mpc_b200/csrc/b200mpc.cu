@@ -12,9 +12,7 @@
 #include "../../include/b200mpc.h"
 #include "mpc_common.cuh"
 #include "mpc_tpp.cuh"
-#ifdef B2MPC_WITH_WPP
 #include "mpc_wpp.cuh"
-#endif
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...)
@@ -46,6 +44,8 @@ struct b2mpc {
     int32_t* stage_hi;
     size_t stage_elems;
     int64_t launches;
+    int kernel;                      // resolved: 1 thread-per-problem, 2 warp-per-problem
+    size_t wpp_smem;
     B2Params prm;
 };
 
@@ -152,6 +152,22 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         return fail(B2MPC_ENOMEM, "staging allocation failed");
     }
     fill_params(h);
+    // kernel selection: the warp-per-problem kernel keeps a whole problem on chip; it needs one lane
+    // per shooting node and its shared-memory block to fit one SM
+    h->wpp_smem = b2_wpp_smem_bytes(N, M);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const bool wpp_ok = (N + 1 <= 32) && (h->wpp_smem <= (size_t)max_smem);
+    if (cfg->kernel == 2 && !wpp_ok) {
+        b2mpc_destroy(h);
+        return fail(B2MPC_EINVAL, "warp-per-problem kernel needs N+1 <= 32 and %zu B <= %d B of shared memory", b2_wpp_smem_bytes(N, M), max_smem);
+    }
+    h->kernel = (cfg->kernel == 1) ? 1 : (cfg->kernel == 2 ? 2 : (wpp_ok ? 2 : 1));
+    if (h->kernel == 2) {
+        cudaError_t e = (M == 5) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
+                                 : cudaFuncSetAttribute(b2_rti_solve_wpp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+        if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
     return B2MPC_OK;
@@ -409,11 +425,15 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     B2Params p = h->prm;
     p.B = (int)batch;
-    const int threads = 64;
-    const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
-    switch (h->M) {
-        case 5: b2_rti_solve_tpp<5><<<blocks, threads, 0, st>>>(p); break;
-        default: b2_rti_solve_tpp<0><<<blocks, threads, 0, st>>>(p); break;
+    if (h->kernel == 2) {
+        const unsigned blocks = (unsigned)batch;          // one warp-CTA per problem
+        if (h->M == 5) b2_rti_solve_wpp<5><<<blocks, 32, h->wpp_smem, st>>>(p);
+        else b2_rti_solve_wpp<0><<<blocks, 32, h->wpp_smem, st>>>(p);
+    } else {
+        const int threads = 64;
+        const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
+        if (h->M == 5) b2_rti_solve_tpp<5><<<blocks, threads, 0, st>>>(p);
+        else b2_rti_solve_tpp<0><<<blocks, threads, 0, st>>>(p);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());

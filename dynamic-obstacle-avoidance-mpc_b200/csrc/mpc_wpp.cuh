@@ -1,0 +1,771 @@
+// mpc_wpp.cuh -- warp-per-problem fused SQP-RTI kernel: the whole solve of one MPC problem stays
+// on chip (shared memory + registers) from linearisation to the full-step update.
+//
+// Same mathematics as mpc_tpp.cuh / the oracle (acados SQP_RTI + HPIPM-style Mehrotra IPM behind
+// src/simulation/robot_ocp_problem.py:195), different mapping:
+//   * stage-parallel phases (linearise, constraint evaluation, residuals, slack/multiplier
+//     elimination, expansion, step length, update): lane k owns shooting node k; reductions
+//     (step length, mu, residual norms) are warp shuffles;
+//   * the sequential backward/forward Riccati sweeps run over the nodes with the 7x7 stage
+//     algebra spread over the lanes (see riccati_*), exchanging through shared memory;
+//   * per-node data live in shared memory as rows [field][node] (conflict-free for lane==node
+//     access, odd row stride for lane==field access).
+// One CTA = one warp = one problem at a time; CTAs pull problems from the batch by blockIdx.
+#pragma once
+#include "mpc_common.cuh"
+
+struct WOff {
+    int sv, hg, rb, lrb, dv, dpi, lamu, lxu, pm, pv, lu;                        // read by the sweeps
+    int lam, t, tinv, dd;                                                       // per constraint (nct rows each)
+    int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrg, lrgsl, lrgsu, esl, esu, dli, dui, xu;
+    int total;
+    __host__ __device__ explicit WOff(int M)
+    {
+        const int nct = 12 + 4 * M;
+        int o = 0;
+        sv = o; o += 10; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
+        lamu = o; o += 3; lxu = o; o += 10; pm = o; o += 15; pv = o; o += 5; lu = o; o += 2;
+        lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
+        b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
+        zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
+        v = o; o += 7; sl = o; o += M; su = o; o += M; pi = o; o += 5; rg = o; o += 7; lrg = o; o += 7;
+        lrgsl = o; o += M; lrgsu = o; o += M; esl = o; o += M; esu = o; o += M; dli = o; o += M; dui = o; o += M;
+        xu = o; o += 6;
+        total = o;
+    }
+};
+
+__host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd row stride
+__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M) { return sizeof(double) * (size_t)WOff(M).total * b2_wpp_stride(N); }
+
+__device__ __forceinline__ double b2_warp_max(double v)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+__device__ __forceinline__ double b2_warp_sum(double v)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+enum { XP_ALPHA = 0, XP_UPDATE = 1, XP_LIN = 2 };
+
+template <int MT>
+struct WppSolver {
+    const B2Params& p;
+    const int b, lane, N, NS, M, nct;
+    double* const sm;
+    const WOff o;
+    const size_t Bm;
+    const int k;            // node owned by this lane
+    const bool act;
+    const int o_lb, o_lg, o_ub, o_ug, o_ls, o_us;
+    int nc;
+    double mu, nrm[4], sum_lt, alpha, S1, S2;
+
+    __device__ WppSolver(const B2Params& p_, int b_, double* sm_)
+        : p(p_), b(b_), lane(threadIdx.x & 31), N(p_.N), NS(b2_wpp_stride(p_.N)), M(MT > 0 ? MT : p_.M),
+          nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), o(MT > 0 ? MT : p_.M), Bm((size_t)p_.Bm),
+          k(threadIdx.x & 31), act((int)(threadIdx.x & 31) <= p_.N),
+          o_lb(0), o_lg(6), o_ub(6 + (MT > 0 ? MT : p_.M)), o_ug(12 + (MT > 0 ? MT : p_.M)),
+          o_ls(12 + 2 * (MT > 0 ? MT : p_.M)), o_us(12 + 3 * (MT > 0 ? MT : p_.M))
+    {
+        nc = 0;
+        for (int kk = 0; kk <= N; kk++) nc += 2 * ((kk < N ? 2 : 0) + ((kk > 0 && kk < N) ? 4 : 0)) + 4 * M;
+    }
+
+    __device__ __forceinline__ double& S(int row, int kk) const { return sm[row * NS + kk]; }
+    __device__ __forceinline__ bool box_on(int s, int kk) const { return s < 2 ? (kk < N) : (kk > 0 && kk < N); }
+    __device__ __forceinline__ double scal(int kk) const { return kk < N ? p.dt : 1.0; }
+    __device__ __forceinline__ void box_bounds(int s, double& lb, double& ub) const
+    {
+        const double xv = S(o.xu + s, k);
+        if (s < 2) { lb = p.lbu[s] - xv; ub = p.ubu[s] - xv; }
+        else { lb = p.lbx[s - 2] - xv; ub = p.ubx[s - 2] - xv; }
+    }
+
+    // ---- preparation + cold-start initialisation: lane k handles node k ----------------------------
+    __device__ void prepare_and_init()
+    {
+        if (act) {
+            double xk[5], uk[2] = {0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b];
+            const double sc = scal(k);
+            const double* yr = p.YREF + ((size_t)k * 6) * Bm + b;
+            if (k < N) {
+                uk[0] = p.U[((size_t)k * 2 + 0) * Bm + b]; uk[1] = p.U[((size_t)k * 2 + 1) * Bm + b];
+                double xn[5], sv[10];
+                if (p.integrator == 1) model_rk4_step(xk, uk, p.dt, xn, sv);
+                else model_gl4_step(xk, uk, p.dt, xn, sv);
+#pragma unroll
+                for (int i = 0; i < 10; i++) S(o.sv + i, k) = sv[i];
+#pragma unroll
+                for (int i = 0; i < 5; i++) S(o.b + i, k) = xn[i] - p.X[((size_t)(k + 1) * 5 + i) * Bm + b];
+                S(o.g + 0, k) = p.Wg[0] * (uk[0] - yr[4 * Bm]);
+                S(o.g + 1, k) = p.Wg[1] * (uk[1] - yr[5 * Bm]);
+                S(o.g + 2, k) = p.Wg[2] * (xk[0] - yr[0 * Bm]);
+                S(o.g + 3, k) = p.Wg[3] * (xk[1] - yr[1 * Bm]);
+                S(o.g + 4, k) = 0.0;
+                S(o.g + 5, k) = p.Wg[5] * (xk[3] - yr[2 * Bm]);
+                S(o.g + 6, k) = p.Wg[6] * (xk[4] - yr[3 * Bm]);
+            } else {
+                S(o.g + 0, k) = 0.0; S(o.g + 1, k) = 0.0;
+                S(o.g + 2, k) = p.Wge[2] * (xk[0] - yr[0 * Bm]);
+                S(o.g + 3, k) = p.Wge[3] * (xk[1] - yr[1 * Bm]);
+                S(o.g + 4, k) = 0.0;
+                S(o.g + 5, k) = p.Wge[5] * (xk[3] - yr[2 * Bm]);
+                S(o.g + 6, k) = p.Wge[6] * (xk[4] - yr[3 * Bm]);
+            }
+            S(o.xu + 0, k) = uk[0]; S(o.xu + 1, k) = uk[1];
+            S(o.xu + 2, k) = xk[0]; S(o.xu + 3, k) = xk[1]; S(o.xu + 4, k) = xk[3]; S(o.xu + 5, k) = xk[4];
+            double v[7] = {0, 0, 0, 0, 0, 0, 0};
+            if (k == 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) v[2 + i] = p.X0[(size_t)i * Bm + b] - xk[i];
+            }
+            for (int i = 0; i < nct; i++) { S(o.lam + i, k) = 0.0; S(o.t + i, k) = 0.0; S(o.tinv + i, k) = 0.0; S(o.dd + i, k) = 0.0; }
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                double lb, ub;
+                box_bounds(s, lb, ub);
+                const int iv = b2_slot2v(s);
+                double tl = -lb + v[iv], tu = ub - v[iv];
+                if (tl < p.thr0) {
+                    if (tu < p.thr0) { v[iv] = 0.5 * (lb + ub); tl = p.thr0; tu = p.thr0; }
+                    else { tl = p.thr0; v[iv] = lb + p.thr0; }
+                } else if (tu < p.thr0) { tu = p.thr0; v[iv] = ub - p.thr0; }
+                S(o.t + o_lb + s, k) = tl; S(o.t + o_ub + s, k) = tu;
+                S(o.lam + o_lb + s, k) = p.mu0 / tl; S(o.lam + o_ub + s, k) = p.mu0 / tu;
+            }
+            for (int j = 0; j < M; j++) {
+                double hval, cx, cy;
+                model_con_h(xk, p.P[((size_t)k * 2 * M + 2 * j) * Bm + b], p.P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b], p.r2, &hval, &cx, &cy);
+                const double s_l = p.SL[((size_t)k * M + j) * Bm + b], s_u = p.SU[((size_t)k * M + j) * Bm + b];
+                const double lg = p.lh - hval - s_l, ug = p.uh - hval + s_u;
+                S(o.cx + j, k) = cx; S(o.cy + j, k) = cy; S(o.lg + j, k) = lg; S(o.ug + j, k) = ug;
+                S(o.sli + j, k) = s_l; S(o.sui + j, k) = s_u;
+                const double zl_in = p.ZL[((size_t)k * M + j) * Bm + b], Zl_in = p.ZZL[((size_t)k * M + j) * Bm + b];
+                S(o.zlq + j, k) = sc * (zl_in + Zl_in * s_l);
+                S(o.Zlq + j, k) = sc * Zl_in;
+                const double cv = cx * v[2] + cy * v[3];
+                double tl = cv - lg, tu = ug - cv;
+                tl = p.thr0 > tl ? p.thr0 : tl;
+                tu = p.thr0 > tu ? p.thr0 : tu;
+                S(o.t + o_lg + j, k) = tl; S(o.t + o_ug + j, k) = tu;
+                S(o.lam + o_lg + j, k) = p.mu0 / tl; S(o.lam + o_ug + j, k) = p.mu0 / tu;
+                S(o.t + o_ls + j, k) = 1.0; S(o.t + o_us + j, k) = 1.0;
+                S(o.lam + o_ls + j, k) = p.mu0; S(o.lam + o_us + j, k) = p.mu0;
+                S(o.sl + j, k) = 0.0; S(o.su + j, k) = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.v + i, k) = v[i];
+#pragma unroll
+            for (int i = 0; i < 5; i++) S(o.pi + i, k) = 0.0;
+        }
+        __syncwarp();
+    }
+
+    // constraint function values minus bounds, g_i(v,s) (so that rd_i = g_i - t_i), node k of this lane
+    __device__ __forceinline__ double g_box_l(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return v[b2_slot2v(s)] - lb; }
+    __device__ __forceinline__ double g_box_u(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return ub - v[b2_slot2v(s)]; }
+
+    // ---- KKT residuals ---------------------------------------------------------------------------
+    __device__ void residuals()
+    {
+        double sum = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+        if (act) {
+            double v[7], rg[7];
+            const double* Hd = k < N ? p.Hd : p.Hde;
+            const double sc = scal(k);
+#pragma unroll
+            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + S(o.g + i, k); }
+            double sv[10];
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, k);
+                double pk[5], bt[7];
+#pragma unroll
+                for (int i = 0; i < 5; i++) pk[i] = S(o.pi + i, k);
+                b2_bat_mul(sv, p.dt, p.dt2h, pk, bt);
+#pragma unroll
+                for (int i = 0; i < 7; i++) rg[i] += bt[i];
+            }
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) rg[2 + i] -= S(o.pi + i, k - 1);
+            }
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                const int iv = b2_slot2v(s);
+                const double ll = S(o.lam + o_lb + s, k), lu_ = S(o.lam + o_ub + s, k);
+                const double tl = S(o.t + o_lb + s, k), tu = S(o.t + o_ub + s, k);
+                rg[iv] += -ll + lu_;
+                const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+                n2 = fmax(n2, fmax(fabs(rdl), fabs(rdu)));
+                const double ml = ll * tl, mu_ = lu_ * tu;
+                n3 = fmax(n3, fmax(fabs(ml), fabs(mu_)));
+                sum += ml; sum += mu_;
+            }
+            const double Zuq = sc * p.Zu;
+            for (int j = 0; j < M; j++) {
+                const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+                const double cv = cx * v[2] + cy * v[3];
+                const double llg = S(o.lam + o_lg + j, k), lug = S(o.lam + o_ug + j, k), lls = S(o.lam + o_ls + j, k), lus = S(o.lam + o_us + j, k);
+                const double tlg = S(o.t + o_lg + j, k), tug = S(o.t + o_ug + j, k), tls = S(o.t + o_ls + j, k), tus = S(o.t + o_us + j, k);
+                const double dl = lug - llg;
+                rg[2] += cx * dl; rg[3] += cy * dl;
+                const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
+                const double sli = S(o.sli + j, k), sui = S(o.sui + j, k);
+                const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - llg - lls;
+                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * sui) - lug - lus;
+                n0 = fmax(n0, fmax(fabs(rgsl), fabs(rgsu)));
+                const double rdlg = cv + s_l - S(o.lg + j, k) - tlg;
+                const double rdug = S(o.ug + j, k) - cv + s_u - tug;
+                const double rdls = s_l + sli - tls;
+                const double rdus = s_u + sui - tus;
+                n2 = fmax(n2, fmax(fmax(fabs(rdlg), fabs(rdug)), fmax(fabs(rdls), fabs(rdus))));
+                const double m0 = llg * tlg, m1 = lug * tug, m2 = lls * tls, m3 = lus * tus;
+                n3 = fmax(n3, fmax(fmax(fabs(m0), fabs(m1)), fmax(fabs(m2), fabs(m3))));
+                sum += m0; sum += m1; sum += m2; sum += m3;
+            }
+            if (k < N) {
+                double rb[5];
+                b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    rb[i] += S(o.b + i, k) - S(o.v + 2 + i, k + 1);
+                    S(o.rb + i, k) = rb[i];
+                    n1 = fmax(n1, fabs(rb[i]));
+                }
+            }
+            if (k == 0) { rg[2] = rg[3] = rg[4] = rg[5] = rg[6] = 0.0; }
+            if (k == N) { rg[0] = rg[1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) { S(o.rg + i, k) = rg[i]; n0 = fmax(n0, fabs(rg[i])); }
+        }
+        // NaN-propagating max: fmax drops NaNs, so carry a flag
+        sum = b2_warp_sum(sum);
+        nrm[0] = b2_warp_max(n0); nrm[1] = b2_warp_max(n1); nrm[2] = b2_warp_max(n2); nrm[3] = b2_warp_max(n3);
+        sum_lt = sum;
+        mu = sum / nc;
+        __syncwarp();
+    }
+
+    // ---- barrier/slack elimination -> condensed node Hessians (lane k), then the Riccati recursion ---
+    __device__ void factorize()
+    {
+        if (act) {
+            const double* Hd = k < N ? p.Hd : p.Hde;
+            const double sc = scal(k);
+            double Hx[7], hxy = 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) Hx[i] = Hd[i] + p.reg_prim;
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                const double til = 1.0 / S(o.t + o_lb + s, k), tiu = 1.0 / S(o.t + o_ub + s, k);
+                S(o.tinv + o_lb + s, k) = til; S(o.tinv + o_ub + s, k) = tiu;
+                Hx[b2_slot2v(s)] += S(o.lam + o_lb + s, k) * til + S(o.lam + o_ub + s, k) * tiu;
+            }
+            const double Zuq = sc * p.Zu;
+            for (int j = 0; j < M; j++) {
+                const double t0 = 1.0 / S(o.t + o_lg + j, k), t1 = 1.0 / S(o.t + o_ug + j, k);
+                const double t2 = 1.0 / S(o.t + o_ls + j, k), t3 = 1.0 / S(o.t + o_us + j, k);
+                S(o.tinv + o_lg + j, k) = t0; S(o.tinv + o_ug + j, k) = t1; S(o.tinv + o_ls + j, k) = t2; S(o.tinv + o_us + j, k) = t3;
+                const double Gl = S(o.lam + o_lg + j, k) * t0, Gu = S(o.lam + o_ug + j, k) * t1;
+                const double Gls = S(o.lam + o_ls + j, k) * t2, Gus = S(o.lam + o_us + j, k) * t3;
+                const double Zlq = S(o.Zlq + j, k);
+                const double Dli = 1.0 / (Zlq + Gl + Gls), Dui = 1.0 / (Zuq + Gu + Gus);
+                S(o.dli + j, k) = Dli; S(o.dui + j, k) = Dui;
+                const double weff = Gl * (Zlq + Gls) * Dli + Gu * (Zuq + Gus) * Dui;
+                const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+                Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.hg + i, k) = Hx[i];
+            S(o.hg + 7, k) = hxy;
+        }
+        __syncwarp();
+        riccati_factorize();
+        __syncwarp();
+    }
+
+    // backward Riccati recursion over the nodes (sequential in k)
+    __device__ void riccati_factorize()
+    {
+        if (lane != 0) return;
+        double Pn[15];
+        for (int kk = N; kk >= 0; kk--) {
+            double Hx[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) Hx[i] = S(o.hg + i, kk);
+            const double hxy = S(o.hg + 7, kk);
+            if (kk == N) {
+#pragma unroll
+                for (int i = 0; i < 15; i++) Pn[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; i++) Pn[b2_sym(i, i)] = Hx[2 + i];
+                Pn[b2_sym(1, 0)] = hxy;
+            } else {
+                double sv[10], Mp[28];
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
+                b2_bat_p_ba(sv, p.dt, p.dt2h, Pn, Mp);
+#pragma unroll
+                for (int i = 0; i < 7; i++) Mp[i * (i + 1) / 2 + i] += Hx[i];
+                Mp[3 * 4 / 2 + 2] += hxy;
+                const double m00 = Mp[0], m10 = Mp[1], m11 = Mp[2];
+                const double l00 = m00 > 0.0 ? sqrt(m00) : 0.0;
+                const double l00i = l00 > 0.0 ? 1.0 / l00 : 0.0;
+                const double l10 = m10 * l00i;
+                const double d11 = m11 - l10 * l10;
+                const double l11 = d11 > 0.0 ? sqrt(d11) : 0.0;
+                const double l11i = l11 > 0.0 ? 1.0 / l11 : 0.0;
+                S(o.lamu + 0, kk) = l00i; S(o.lamu + 1, kk) = l10; S(o.lamu + 2, kk) = l11i;
+                if (kk > 0) {
+                    double L0[5], L1[5];
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        const int r = 2 + i;
+                        L0[i] = Mp[r * (r + 1) / 2 + 0] * l00i;
+                        L1[i] = (Mp[r * (r + 1) / 2 + 1] - L0[i] * l10) * l11i;
+                        S(o.lxu + 2 * i, kk) = L0[i]; S(o.lxu + 2 * i + 1, kk) = L1[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; i++)
+#pragma unroll
+                        for (int j = 0; j <= i; j++) {
+                            const int r = 2 + i, c = 2 + j;
+                            Pn[b2_sym(i, j)] = Mp[r * (r + 1) / 2 + c] - L0[i] * L0[j] - L1[i] * L1[j];
+                        }
+                }
+            }
+            if (kk > 0) {
+#pragma unroll
+                for (int i = 0; i < 15; i++) S(o.pm + i, kk) = Pn[i];
+            }
+        }
+    }
+
+    __device__ __forceinline__ double rm_of(int kind, double l, double t, double dd, double smu) const
+    {
+        if (kind == 0) return l * t;
+        if (kind == 1) return l * t + dd - smu;
+        if (kind == 2) return l * t - smu;
+        return 0.0;
+    }
+
+    // node-local part of a solve: condensed gradient of node k for right-hand side `kind`
+    __device__ void solve_prep(int kind, double smu)
+    {
+        if (act) {
+            const bool itr = (kind == 3);
+            const double sc = scal(k);
+            double v[7], gt[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = S((itr ? o.lrg : o.rg) + i, k); }
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k) || itr) continue;
+                const int il = o_lb + s, iu = o_ub + s;
+                const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
+                const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+                const double ql = (rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * rdl) * S(o.tinv + il, k);
+                const double qu = (rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * rdu) * S(o.tinv + iu, k);
+                gt[b2_slot2v(s)] += ql - qu;
+            }
+            const double Zuq = sc * p.Zu;
+            for (int j = 0; j < M; j++) {
+                double rhol, rhou, q0, q1;
+                slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
+                const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
+                const double coef = (q0 - G0 * rhol * S(o.dli + j, k)) - (q1 - G1 * rhou * S(o.dui + j, k));
+                gt[2] += S(o.cx + j, k) * coef;
+                gt[3] += S(o.cy + j, k) * coef;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.hg + i, k) = gt[i];
+        }
+        __syncwarp();
+    }
+
+    // rho_l, rho_u (slack-elimination right-hand sides) and q_lg, q_ug of obstacle j at node k
+    __device__ __forceinline__ void slack_rho(int kind, double smu, int j, const double* v, double Zuq, double sc,
+                                              double& rhol, double& rhou, double& q0, double& q1) const
+    {
+        const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
+        if (kind == 3) {
+            q0 = q1 = 0.0;
+            rhol = S(o.lrgsl + j, k);
+            rhou = S(o.lrgsu + j, k);
+            return;
+        }
+        const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
+        const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
+        const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
+        const double cv = S(o.cx + j, k) * v[2] + S(o.cy + j, k) * v[3];
+        const double rd0 = cv + s_l - S(o.lg + j, k) - t0;
+        const double rd1 = S(o.ug + j, k) - cv + s_u - t1;
+        const double rd2 = s_l + S(o.sli + j, k) - t2;
+        const double rd3 = s_u + S(o.sui + j, k) - t3;
+        q0 = (rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * rd0) * S(o.tinv + i0, k);
+        q1 = (rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * rd1) * S(o.tinv + i1, k);
+        const double q2 = (rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * rd2) * S(o.tinv + i2, k);
+        const double q3 = (rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * rd3) * S(o.tinv + i3, k);
+        const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
+        const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
+        // esl/esu: slack right-hand sides added by iterative refinement of this step
+        rhol = rgsl + S(o.esl + j, k) + q0 + q2;
+        rhou = rgsu + S(o.esu + j, k) + q1 + q3;
+    }
+
+    // backward + forward vector sweeps with the current factorisation (sequential in k);
+    // kind 3 ACCUMULATES the correction into dv/dpi
+    __device__ void riccati_solve(int kind)
+    {
+        if (lane != 0) return;
+        const bool itr = (kind == 3);
+        const int oRB = itr ? o.lrb : o.rb;
+        double pn[5] = {0, 0, 0, 0, 0};
+        for (int kk = N; kk >= 0; kk--) {
+            double gt[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, kk);
+            if (kk < N) {
+                double sv[10], Pn[15], rb[5], y[5], bt[7];
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
+#pragma unroll
+                for (int i = 0; i < 15; i++) Pn[i] = S(o.pm + i, kk + 1);
+#pragma unroll
+                for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, kk);
+                b2_symv(Pn, rb, y);
+#pragma unroll
+                for (int i = 0; i < 5; i++) y[i] += pn[i];
+                b2_bat_mul(sv, p.dt, p.dt2h, y, bt);
+#pragma unroll
+                for (int i = 0; i < 7; i++) gt[i] += bt[i];
+                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+                const double lu0 = gt[0] * l00i;
+                const double lu1 = (gt[1] - l10 * lu0) * l11i;
+                S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1;
+                if (kk > 0) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) pn[i] = gt[2 + i] - S(o.lxu + 2 * i, kk) * lu0 - S(o.lxu + 2 * i + 1, kk) * lu1;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; i++) pn[i] = gt[2 + i];
+            }
+            if (kk > 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) S(o.pv + i, kk) = pn[i];
+            }
+        }
+        double dx[5] = {0, 0, 0, 0, 0};
+        for (int kk = 0; kk <= N; kk++) {
+            double dv[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 5; i++) dv[2 + i] = dx[i];
+            if (kk < N) {
+                double sv[10];
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
+                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+                double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
+                if (kk > 0) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) { r0 += S(o.lxu + 2 * i, kk) * dx[i]; r1 += S(o.lxu + 2 * i + 1, kk) * dx[i]; }
+                }
+                r0 = -r0; r1 = -r1;
+                dv[1] = r1 * l11i;
+                dv[0] = (r0 - l10 * dv[1]) * l00i;
+                double xn[5], Pn[15], dpi[5];
+                b2_ba_mul(sv, p.dt, p.dt2h, dv, xn);
+#pragma unroll
+                for (int i = 0; i < 5; i++) xn[i] += S(oRB + i, kk);
+#pragma unroll
+                for (int i = 0; i < 15; i++) Pn[i] = S(o.pm + i, kk + 1);
+                b2_symv(Pn, xn, dpi);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    dpi[i] += S(o.pv + i, kk + 1);
+                    if (itr) S(o.dpi + i, kk) += dpi[i]; else S(o.dpi + i, kk) = dpi[i];
+                    dx[i] = xn[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) { if (itr) S(o.dv + i, kk) += dv[i]; else S(o.dv + i, kk) = dv[i]; }
+        }
+    }
+
+    // node-local expansion of the (total) step of node k: ds, dt, dlam of every constraint, consumed
+    // on the fly.  MODE XP_ALPHA: step-length / mu_aff reductions (+ store dt*dlam for kind 0);
+    // XP_UPDATE: apply the step with length a; XP_LIN: assemble the linear-system residual.
+    template <int MODE>
+    __device__ __forceinline__ void expand(int kind, double smu, double a, double& ap, double& ad, double& s1, double& s2,
+                                           double* lrg, double& ln0)
+    {
+        const double sc = scal(k);
+        const double Zuq = sc * p.Zu;
+        double v[7], dv[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); dv[i] = S(o.dv + i, k); }
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            if (!box_on(s, k)) continue;
+            const int iv = b2_slot2v(s);
+            const int il = o_lb + s, iu = o_ub + s;
+            const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
+            const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+            const double dtl = dv[iv] + rdl, dtu = -dv[iv] + rdu;
+            const double dll = -(rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * dtl) * S(o.tinv + il, k);
+            const double dlu = -(rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * dtu) * S(o.tinv + iu, k);
+            consume<MODE>(kind, il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
+            consume<MODE>(kind, iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
+            if (MODE == XP_LIN) lrg[iv] += -dll + dlu;
+        }
+        for (int j = 0; j < M; j++) {
+            const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
+            double rhol, rhou, q0, q1;
+            slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
+            const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+            const double cdv = cx * dv[2] + cy * dv[3];
+            const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
+            const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
+            const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
+            const double dsl = -(l0 * ti0 * cdv + rhol) * S(o.dli + j, k);
+            const double dsu = -(-l1 * ti1 * cdv + rhou) * S(o.dui + j, k);
+            const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
+            const double cv = cx * v[2] + cy * v[3];
+            const double rd0 = cv + s_l - S(o.lg + j, k) - t0;
+            const double rd1 = S(o.ug + j, k) - cv + s_u - t1;
+            const double rd2 = s_l + S(o.sli + j, k) - t2;
+            const double rd3 = s_u + S(o.sui + j, k) - t3;
+            const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
+            const double dl0 = -(rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * dt0) * ti0;
+            const double dl1 = -(rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * dt1) * ti1;
+            const double dl2 = -(rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * dt2) * ti2;
+            const double dl3 = -(rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * dt3) * ti3;
+            consume<MODE>(kind, i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
+            consume<MODE>(kind, i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
+            consume<MODE>(kind, i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
+            consume<MODE>(kind, i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
+            if (MODE == XP_UPDATE) { S(o.sl + j, k) = s_l + a * dsl; S(o.su + j, k) = s_u + a * dsu; }
+            if (MODE == XP_LIN) {
+                const double dl = dl1 - dl0;
+                lrg[2] += cx * dl; lrg[3] += cy * dl;
+                // slack rows of the linear system: Z ds + (rgs + es) - dlam_g - dlam_s
+                const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
+                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
+                const double a0 = S(o.Zlq + j, k) * dsl + rgsl - dl0 - dl2;
+                const double a1 = Zuq * dsu + rgsu - dl1 - dl3;
+                S(o.lrgsl + j, k) = a0; S(o.lrgsu + j, k) = a1;
+                ln0 = fmax(ln0, fmax(fabs(a0), fabs(a1)));
+            }
+        }
+    }
+
+    template <int MODE>
+    __device__ __forceinline__ void consume(int kind, int i, double l, double t, double dti, double dli, double a,
+                                            double& ap, double& ad, double& s1, double& s2)
+    {
+        if (MODE == XP_ALPHA) {
+            if (kind == 0) S(o.dd + i, k) = dti * dli;
+            if (ad * dli > l) ad = l / dli;
+            if (ap * dti > t) ap = t / dti;
+            s1 += l * dti + t * dli;
+            s2 += dli * dti;
+        } else if (MODE == XP_UPDATE) {
+            double ln = l + a * dli, tn = t + a * dti;
+            if (ln <= p.lam_min) ln = p.lam_min;
+            if (tn <= p.t_min) tn = p.t_min;
+            S(o.lam + i, k) = ln; S(o.t + i, k) = tn;
+        }
+    }
+
+    // solve for a base right-hand side (kind 0 affine, 1 corrector, 2 centering) + step-length reductions
+    __device__ void solve_base(int kind, double smu)
+    {
+        if (act) {
+            for (int j = 0; j < M; j++) { S(o.esl + j, k) = 0.0; S(o.esu + j, k) = 0.0; }
+        }
+        solve_prep(kind, smu);
+        riccati_solve(kind);
+        __syncwarp();
+        step_length(kind, smu);
+    }
+
+    // one iterative-refinement step on the current direction: solve for the linear residual, accumulate
+    __device__ void solve_refine(int base_kind, double smu)
+    {
+        solve_prep(3, 0.0);
+        riccati_solve(3);
+        __syncwarp();
+        if (act) {
+            for (int j = 0; j < M; j++) { S(o.esl + j, k) += S(o.lrgsl + j, k); S(o.esu + j, k) += S(o.lrgsu + j, k); }
+        }
+        __syncwarp();
+        step_length(base_kind, smu);
+    }
+
+    __device__ void step_length(int kind, double smu)
+    {
+        double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
+        if (act) expand<XP_ALPHA>(kind, smu, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        // max of the negative reciprocals == min of the admissible step lengths (HPIPM convention)
+        ap = b2_warp_max(ap); ad = b2_warp_max(ad);
+        S1 = b2_warp_sum(s1); S2 = b2_warp_sum(s2);
+        alpha = -(ap > ad ? ap : ad);
+        __syncwarp();
+    }
+
+    __device__ void lin_residuals(int kind, double smu, double lnrm[2])
+    {
+        double ln0 = 0.0, ln1 = 0.0;
+        if (act) {
+            const double* Hd = k < N ? p.Hd : p.Hde;
+            double dv[7], lrg[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) { dv[i] = S(o.dv + i, k); lrg[i] = S(o.rg + i, k) + Hd[i] * dv[i]; }
+            double sv[10];
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, k);
+                double dp[5], bt[7];
+#pragma unroll
+                for (int i = 0; i < 5; i++) dp[i] = S(o.dpi + i, k);
+                b2_bat_mul(sv, p.dt, p.dt2h, dp, bt);
+#pragma unroll
+                for (int i = 0; i < 7; i++) lrg[i] += bt[i];
+            }
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) lrg[2 + i] -= S(o.dpi + i, k - 1);
+            }
+            double ap = 0, ad = 0, s1 = 0, s2 = 0;
+            expand<XP_LIN>(kind, smu, 0.0, ap, ad, s1, s2, lrg, ln0);
+            if (k < N) {
+                double lrb[5];
+                b2_ba_mul(sv, p.dt, p.dt2h, dv, lrb);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    lrb[i] += S(o.rb + i, k) - S(o.dv + 2 + i, k + 1);
+                    S(o.lrb + i, k) = lrb[i];
+                    ln1 = fmax(ln1, fabs(lrb[i]));
+                }
+            }
+            if (k == 0) { lrg[2] = lrg[3] = lrg[4] = lrg[5] = lrg[6] = 0.0; }
+            if (k == N) { lrg[0] = lrg[1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) { S(o.lrg + i, k) = lrg[i]; ln0 = fmax(ln0, fabs(lrg[i])); }
+        }
+        lnrm[0] = b2_warp_max(ln0); lnrm[1] = b2_warp_max(ln1);
+        __syncwarp();
+    }
+
+    __device__ void update(int kind, double smu, double a)
+    {
+        if (act) {
+            double ap = 0, ad = 0, s1 = 0, s2 = 0, dummy = 0;
+            expand<XP_UPDATE>(kind, smu, a, ap, ad, s1, s2, nullptr, dummy);
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.v + i, k) += a * S(o.dv + i, k);
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) S(o.pi + i, k) += a * S(o.dpi + i, k);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- the whole RTI call -------------------------------------------------------------------------
+    __device__ void run()
+    {
+        prepare_and_init();
+        residuals();
+        alpha = 1.0;
+        int kk = 0, n_itref = 0;
+        const double inv_nc = 1.0 / nc;
+        for (; kk < p.qp_iter_max && alpha > p.alpha_min &&
+               (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max); kk++) {
+            factorize();
+            int base = 0;
+            double smu = 0.0;
+            solve_base(0, 0.0);
+            if (p.pred_corr) {
+                double mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
+                const double tmp = mu_aff / mu;
+                smu = tmp * tmp * tmp * mu;
+                smu = smu > p.tau_min ? smu : p.tau_min;
+                solve_base(1, smu); base = 1;
+                if (p.cond_pred_corr) {
+                    const double mu_aff0 = mu_aff;
+                    mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
+                    if (mu_aff > 2.0 * mu_aff0) { solve_base(2, smu); base = 2; }
+                }
+                for (int it = 0; it < p.itref_corr_max; it++) {
+                    double lnrm[2];
+                    lin_residuals(base, smu, lnrm);
+                    if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
+                    solve_refine(base, smu);
+                    n_itref++;
+                }
+            }
+            double a = alpha;
+            if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+            update(base, smu, a);
+            residuals();
+        }
+        int qs;
+        if (kk == p.qp_iter_max) qs = 1;
+        else if (alpha <= p.alpha_min) qs = 2;
+        else if (mu != mu || nrm[0] != nrm[0] || nrm[1] != nrm[1] || nrm[2] != nrm[2] || nrm[3] != nrm[3]) qs = 3;
+        else qs = 0;
+        const int status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate untouched
+        if (act) {
+            if (status == 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += S(o.v + 2 + i, k);
+                if (k < N) {
+                    p.U[((size_t)k * 2 + 0) * Bm + b] += S(o.v + 0, k);
+                    p.U[((size_t)k * 2 + 1) * Bm + b] += S(o.v + 1, k);
+                }
+                for (int j = 0; j < M; j++) {
+                    p.SL[((size_t)k * M + j) * Bm + b] += S(o.sl + j, k);
+                    p.SU[((size_t)k * M + j) * Bm + b] += S(o.su + j, k);
+                }
+            }
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = S(o.pi + i, k);
+            }
+            for (int i = 0; i < nct; i++) {
+                p.LAM[((size_t)k * nct + i) * Bm + b] = S(o.lam + i, k);
+                p.T[((size_t)k * nct + i) * Bm + b] = S(o.t + i, k);
+            }
+        }
+        if (lane == 0) {
+            p.STATUS[b] = status; p.QP_ITER[b] = kk; p.QP_STATUS[b] = qs;
+            p.STATS[0 * Bm + b] = nrm[0]; p.STATS[1 * Bm + b] = nrm[1]; p.STATS[2 * Bm + b] = nrm[2]; p.STATS[3 * Bm + b] = nrm[3];
+            p.STATS[4 * Bm + b] = mu; p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
+        }
+        __syncwarp();
+    }
+};
+
+template <int MT>
+__global__ void __launch_bounds__(32) b2_rti_solve_wpp(const B2Params p)
+{
+    extern __shared__ double b2_smem[];
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        WppSolver<MT> s(p, b, b2_smem);
+        s.run();
+    }
+}
