@@ -164,8 +164,9 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     }
     h->kernel = (cfg->kernel == 1) ? 1 : (cfg->kernel == 2 ? 2 : (wpp_ok ? 2 : 1));
     if (h->kernel == 2) {
-        cudaError_t e = (M == 5) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
-                                 : cudaFuncSetAttribute(b2_rti_solve_wpp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+        cudaError_t e = (M == 5 && N == 20) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
+                      : (M == 5)            ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
+                                            : cudaFuncSetAttribute(b2_rti_solve_wpp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
         if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     }
     CUDA_TRY(cudaDeviceSynchronize());
@@ -427,8 +428,9 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     p.B = (int)batch;
     if (h->kernel == 2) {
         const unsigned blocks = (unsigned)batch;          // one warp-CTA per problem
-        if (h->M == 5) b2_rti_solve_wpp<5><<<blocks, 32, h->wpp_smem, st>>>(p);
-        else b2_rti_solve_wpp<0><<<blocks, 32, h->wpp_smem, st>>>(p);
+        if (h->M == 5 && h->N == 20) b2_rti_solve_wpp<5, 20><<<blocks, 32, h->wpp_smem, st>>>(p);
+        else if (h->M == 5) b2_rti_solve_wpp<5, 0><<<blocks, 32, h->wpp_smem, st>>>(p);
+        else b2_rti_solve_wpp<0, 0><<<blocks, 32, h->wpp_smem, st>>>(p);
     } else {
         const int threads = 64;
         const unsigned blocks = (unsigned)((batch + threads - 1) / threads);

@@ -3,33 +3,48 @@
 //
 // Same mathematics as mpc_tpp.cuh / the oracle (acados SQP_RTI + HPIPM-style Mehrotra IPM behind
 // src/simulation/robot_ocp_problem.py:195), different mapping:
-//   * stage-parallel phases (linearise, constraint evaluation, residuals, slack/multiplier
+//   * node-parallel phases (linearise, constraint evaluation, residuals, multiplier/slack
 //     elimination, expansion, step length, update): lane k owns shooting node k; reductions
 //     (step length, mu, residual norms) are warp shuffles;
-//   * the sequential backward/forward Riccati sweeps run over the nodes with the 7x7 stage
-//     algebra spread over the lanes (see riccati_*), exchanging through shared memory;
-//   * per-node data live in shared memory as rows [field][node] (conflict-free for lane==node
-//     access, odd row stride for lane==field access).
-// One CTA = one warp = one problem at a time; CTAs pull problems from the batch by blockIdx.
+//   * the sequential backward/forward Riccati sweeps walk the nodes with the 7x7 node algebra
+//     spread over the lanes: lane e < 28 owns entry (i,j) of the symmetric Riccati matrix in the
+//     factorisation, lanes 0..6 own rows/columns in the vector sweeps; exchange by shuffles;
+//   * per-node data live in shared memory as rows [field][node]: lane==node accesses are
+//     conflict-free, the odd row stride keeps lane==field accesses conflict-free too.
+// One CTA = one warp = one problem at a time.
+//
+// Numerical note (why dlam is STORED and never re-derived): dlam_i = -(rm_i + lam_i dt_i)/t_i carries
+// lam/t up to ~1e18 on slack bounds, so iterative refinement only works if the correction is added
+// to the stored dlam; re-deriving dlam from the refined dv would draw a fresh rounding sample.
 #pragma once
 #include "mpc_common.cuh"
 
+// table of [B A] (5 x 7, rows x+, cols [u_a,u_alpha,x,y,psi,v,omega]) as indices into the extended
+// per-node vector ext = [sv0..sv9, 1, 0, h, h^2/2]  (pattern checked in mpc_common.cuh)
+__constant__ unsigned char B2_BATAB[5][7] = {
+    {SV_B00, SV_B01, 10, 11, SV_A02, SV_A03, SV_A04},
+    {SV_B10, SV_B11, 11, 10, SV_A12, SV_A13, SV_A14},
+    {11, 13, 11, 11, 10, 11, 12},
+    {12, 11, 11, 11, 11, 10, 11},
+    {11, 12, 11, 11, 11, 11, 10},
+};
+
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, lamu, lxu, pm, pv, lu;                        // read by the sweeps
-    int lam, t, tinv, dd;                                                       // per constraint (nct rows each)
-    int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrg, lrgsl, lrgsu, esl, esu, dli, dui, xu;
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, pm, pv, lu;               // used by the sweeps
+    int lam, t, tinv, dd;                                                       // per constraint (nct rows each); dd doubles as dlam
+    int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrgsl, lrgsu, dsl, dsu, dli, dui, xu;
     int total;
     __host__ __device__ explicit WOff(int M)
     {
         const int nct = 12 + 4 * M;
         int o = 0;
-        sv = o; o += 10; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
-        lamu = o; o += 3; lxu = o; o += 10; pm = o; o += 15; pv = o; o += 5; lu = o; o += 2;
+        sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
+        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; pm = o; o += 15; pv = o; o += 5; lu = o; o += 2;
         lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
         b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
         zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
-        v = o; o += 7; sl = o; o += M; su = o; o += M; pi = o; o += 5; rg = o; o += 7; lrg = o; o += 7;
-        lrgsl = o; o += M; lrgsu = o; o += M; esl = o; o += M; esu = o; o += M; dli = o; o += M; dui = o; o += M;
+        v = o; o += 7; sl = o; o += M; su = o; o += M; pi = o; o += 5; rg = o; o += 7;
+        lrgsl = o; o += M; lrgsu = o; o += M; dsl = o; o += M; dsu = o; o += M; dli = o; o += M; dui = o; o += M;
         xu = o; o += 6;
         total = o;
     }
@@ -50,10 +65,12 @@ __device__ __forceinline__ double b2_warp_sum(double v)
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     return v;
 }
+__device__ __forceinline__ double b2_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-enum { XP_ALPHA = 0, XP_UPDATE = 1, XP_LIN = 2 };
+// expansion modes
+enum { XP_SOLVE = 0, XP_REFINE = 1, XP_UPDATE = 2, XP_LIN = 3 };
 
-template <int MT>
+template <int MT, int NT>
 struct WppSolver {
     const B2Params& p;
     const int b, lane, N, NS, M, nct;
@@ -67,9 +84,9 @@ struct WppSolver {
     double mu, nrm[4], sum_lt, alpha, S1, S2;
 
     __device__ WppSolver(const B2Params& p_, int b_, double* sm_)
-        : p(p_), b(b_), lane(threadIdx.x & 31), N(p_.N), NS(b2_wpp_stride(p_.N)), M(MT > 0 ? MT : p_.M),
+        : p(p_), b(b_), lane(threadIdx.x & 31), N(NT > 0 ? NT : p_.N), NS(b2_wpp_stride(NT > 0 ? NT : p_.N)), M(MT > 0 ? MT : p_.M),
           nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), o(MT > 0 ? MT : p_.M), Bm((size_t)p_.Bm),
-          k(threadIdx.x & 31), act((int)(threadIdx.x & 31) <= p_.N),
+          k(threadIdx.x & 31), act((int)(threadIdx.x & 31) <= (NT > 0 ? NT : p_.N)),
           o_lb(0), o_lg(6), o_ub(6 + (MT > 0 ? MT : p_.M)), o_ug(12 + (MT > 0 ? MT : p_.M)),
           o_ls(12 + 2 * (MT > 0 ? MT : p_.M)), o_us(12 + 3 * (MT > 0 ? MT : p_.M))
     {
@@ -96,13 +113,12 @@ struct WppSolver {
             for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b];
             const double sc = scal(k);
             const double* yr = p.YREF + ((size_t)k * 6) * Bm + b;
+            double sv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (k < N) {
                 uk[0] = p.U[((size_t)k * 2 + 0) * Bm + b]; uk[1] = p.U[((size_t)k * 2 + 1) * Bm + b];
-                double xn[5], sv[10];
+                double xn[5];
                 if (p.integrator == 1) model_rk4_step(xk, uk, p.dt, xn, sv);
                 else model_gl4_step(xk, uk, p.dt, xn, sv);
-#pragma unroll
-                for (int i = 0; i < 10; i++) S(o.sv + i, k) = sv[i];
 #pragma unroll
                 for (int i = 0; i < 5; i++) S(o.b + i, k) = xn[i] - p.X[((size_t)(k + 1) * 5 + i) * Bm + b];
                 S(o.g + 0, k) = p.Wg[0] * (uk[0] - yr[4 * Bm]);
@@ -120,6 +136,9 @@ struct WppSolver {
                 S(o.g + 5, k) = p.Wge[5] * (xk[3] - yr[2 * Bm]);
                 S(o.g + 6, k) = p.Wge[6] * (xk[4] - yr[3 * Bm]);
             }
+#pragma unroll
+            for (int i = 0; i < 10; i++) S(o.sv + i, k) = sv[i];
+            S(o.sv + 10, k) = 1.0; S(o.sv + 11, k) = 0.0; S(o.sv + 12, k) = p.dt; S(o.sv + 13, k) = p.dt2h;
             S(o.xu + 0, k) = uk[0]; S(o.xu + 1, k) = uk[1];
             S(o.xu + 2, k) = xk[0]; S(o.xu + 3, k) = xk[1]; S(o.xu + 4, k) = xk[3]; S(o.xu + 5, k) = xk[4];
             double v[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -142,6 +161,7 @@ struct WppSolver {
                 S(o.t + o_lb + s, k) = tl; S(o.t + o_ub + s, k) = tu;
                 S(o.lam + o_lb + s, k) = p.mu0 / tl; S(o.lam + o_ub + s, k) = p.mu0 / tu;
             }
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 double hval, cx, cy;
                 model_con_h(xk, p.P[((size_t)k * 2 * M + 2 * j) * Bm + b], p.P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b], p.r2, &hval, &cx, &cy);
@@ -170,7 +190,7 @@ struct WppSolver {
         __syncwarp();
     }
 
-    // constraint function values minus bounds, g_i(v,s) (so that rd_i = g_i - t_i), node k of this lane
+    // g_i(v,s) of the box constraints (rd_i = g_i - t_i)
     __device__ __forceinline__ double g_box_l(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return v[b2_slot2v(s)] - lb; }
     __device__ __forceinline__ double g_box_u(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return ub - v[b2_slot2v(s)]; }
 
@@ -213,6 +233,7 @@ struct WppSolver {
                 sum += ml; sum += mu_;
             }
             const double Zuq = sc * p.Zu;
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
                 const double cv = cx * v[2] + cy * v[3];
@@ -249,7 +270,6 @@ struct WppSolver {
 #pragma unroll
             for (int i = 0; i < 7; i++) { S(o.rg + i, k) = rg[i]; n0 = fmax(n0, fabs(rg[i])); }
         }
-        // NaN-propagating max: fmax drops NaNs, so carry a flag
         sum = b2_warp_sum(sum);
         nrm[0] = b2_warp_max(n0); nrm[1] = b2_warp_max(n1); nrm[2] = b2_warp_max(n2); nrm[3] = b2_warp_max(n3);
         sum_lt = sum;
@@ -274,6 +294,7 @@ struct WppSolver {
                 Hx[b2_slot2v(s)] += S(o.lam + o_lb + s, k) * til + S(o.lam + o_ub + s, k) * tiu;
             }
             const double Zuq = sc * p.Zu;
+#pragma unroll 1
             for (int j = 0; j < M; j++) {
                 const double t0 = 1.0 / S(o.t + o_lg + j, k), t1 = 1.0 / S(o.t + o_ug + j, k);
                 const double t2 = 1.0 / S(o.t + o_ls + j, k), t3 = 1.0 / S(o.t + o_us + j, k);
@@ -293,63 +314,66 @@ struct WppSolver {
         }
         __syncwarp();
         riccati_factorize();
-        __syncwarp();
     }
 
-    // backward Riccati recursion over the nodes (sequential in k)
+    // backward Riccati recursion, sequential in the node index, lane e<28 owns entry (mi,mj) of
+    // M = Htilde + [B A]^T P+ [B A]; 2x2 control block factorised redundantly by all lanes
     __device__ void riccati_factorize()
     {
-        if (lane != 0) return;
-        double Pn[15];
+        const int e = lane < 28 ? lane : 0;
+        int mi = 0;
+        while ((mi + 1) * (mi + 2) / 2 <= e) mi++;
+        const int mj = e - mi * (mi + 1) / 2;
+        int ci[5], cj[5];
+#pragma unroll
+        for (int r = 0; r < 5; r++) { ci[r] = o.sv + B2_BATAB[r][mi]; cj[r] = o.sv + B2_BATAB[r][mj]; }
+        const int src_i0 = mi * (mi + 1) / 2, src_i1 = mi >= 1 ? src_i0 + 1 : 0;
+        const int src_j0 = mj * (mj + 1) / 2, src_j1 = mj >= 1 ? src_j0 + 1 : 0;
+        const bool xx = lane < 28 && mi >= 2 && mj >= 2;
+        const bool xu = lane < 28 && mi >= 2 && mj < 2;
+        const int prow = xx ? o.pm + b2_sym(mi - 2, mj - 2) : 0;
+        const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
         for (int kk = N; kk >= 0; kk--) {
-            double Hx[7];
+            double m = 0.0;
+            if (mi == mj) m = S(o.hg + mi, kk);
+            if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
+            if (kk < N) {
+                double P[15], w[5], a[5], c[5];
 #pragma unroll
-            for (int i = 0; i < 7; i++) Hx[i] = S(o.hg + i, kk);
-            const double hxy = S(o.hg + 7, kk);
-            if (kk == N) {
+                for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, kk + 1);
 #pragma unroll
-                for (int i = 0; i < 15; i++) Pn[i] = 0.0;
+                for (int r = 0; r < 5; r++) { a[r] = S(ci[r], kk); c[r] = S(cj[r], kk); }
 #pragma unroll
-                for (int i = 0; i < 5; i++) Pn[b2_sym(i, i)] = Hx[2 + i];
-                Pn[b2_sym(1, 0)] = hxy;
-            } else {
-                double sv[10], Mp[28];
+                for (int r = 0; r < 5; r++) {
+                    double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
-                b2_bat_p_ba(sv, p.dt, p.dt2h, Pn, Mp);
+                    for (int q = 0; q < 5; q++) acc += P[b2_sym(r, q)] * c[q];
+                    w[r] = acc;
+                }
+                double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < 7; i++) Mp[i * (i + 1) / 2 + i] += Hx[i];
-                Mp[3 * 4 / 2 + 2] += hxy;
-                const double m00 = Mp[0], m10 = Mp[1], m11 = Mp[2];
+                for (int r = 0; r < 5; r++) acc += a[r] * w[r];
+                m += acc;
+                const double m00 = b2_bcast(m, 0), m10 = b2_bcast(m, 1), m11 = b2_bcast(m, 2);
                 const double l00 = m00 > 0.0 ? sqrt(m00) : 0.0;
                 const double l00i = l00 > 0.0 ? 1.0 / l00 : 0.0;
                 const double l10 = m10 * l00i;
                 const double d11 = m11 - l10 * l10;
                 const double l11 = d11 > 0.0 ? sqrt(d11) : 0.0;
                 const double l11i = l11 > 0.0 ? 1.0 / l11 : 0.0;
-                S(o.lamu + 0, kk) = l00i; S(o.lamu + 1, kk) = l10; S(o.lamu + 2, kk) = l11i;
+                const double mi0 = b2_bcast(m, src_i0), mi1 = b2_bcast(m, src_i1);
+                const double mj0 = b2_bcast(m, src_j0), mj1 = b2_bcast(m, src_j1);
+                const double Li0 = mi0 * l00i, Li1 = (mi1 - Li0 * l10) * l11i;
+                const double Lj0 = mj0 * l00i, Lj1 = (mj1 - Lj0 * l10) * l11i;
+                if (lane == 0) { S(o.lamu + 0, kk) = l00i; S(o.lamu + 1, kk) = l10; S(o.lamu + 2, kk) = l11i; }
                 if (kk > 0) {
-                    double L0[5], L1[5];
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const int r = 2 + i;
-                        L0[i] = Mp[r * (r + 1) / 2 + 0] * l00i;
-                        L1[i] = (Mp[r * (r + 1) / 2 + 1] - L0[i] * l10) * l11i;
-                        S(o.lxu + 2 * i, kk) = L0[i]; S(o.lxu + 2 * i + 1, kk) = L1[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 5; i++)
-#pragma unroll
-                        for (int j = 0; j <= i; j++) {
-                            const int r = 2 + i, c = 2 + j;
-                            Pn[b2_sym(i, j)] = Mp[r * (r + 1) / 2 + c] - L0[i] * L0[j] - L1[i] * L1[j];
-                        }
+                    if (xx) S(prow, kk) = m - Li0 * Lj0 - Li1 * Lj1;
+                    if (xu) S(lrow, kk) = (mj == 0) ? Li0 : Li1;
                 }
+            } else {
+                if (xx) S(prow, kk) = m;
             }
-            if (kk > 0) {
-#pragma unroll
-                for (int i = 0; i < 15; i++) S(o.pm + i, kk) = Pn[i];
-            }
+            __syncwarp();
         }
     }
 
@@ -357,55 +381,14 @@ struct WppSolver {
     {
         if (kind == 0) return l * t;
         if (kind == 1) return l * t + dd - smu;
-        if (kind == 2) return l * t - smu;
-        return 0.0;
+        return l * t - smu;
     }
 
-    // node-local part of a solve: condensed gradient of node k for right-hand side `kind`
-    __device__ void solve_prep(int kind, double smu)
-    {
-        if (act) {
-            const bool itr = (kind == 3);
-            const double sc = scal(k);
-            double v[7], gt[7];
-#pragma unroll
-            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = S((itr ? o.lrg : o.rg) + i, k); }
-#pragma unroll
-            for (int s = 0; s < 6; s++) {
-                if (!box_on(s, k) || itr) continue;
-                const int il = o_lb + s, iu = o_ub + s;
-                const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
-                const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
-                const double ql = (rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * rdl) * S(o.tinv + il, k);
-                const double qu = (rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * rdu) * S(o.tinv + iu, k);
-                gt[b2_slot2v(s)] += ql - qu;
-            }
-            const double Zuq = sc * p.Zu;
-            for (int j = 0; j < M; j++) {
-                double rhol, rhou, q0, q1;
-                slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
-                const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
-                const double coef = (q0 - G0 * rhol * S(o.dli + j, k)) - (q1 - G1 * rhou * S(o.dui + j, k));
-                gt[2] += S(o.cx + j, k) * coef;
-                gt[3] += S(o.cy + j, k) * coef;
-            }
-#pragma unroll
-            for (int i = 0; i < 7; i++) S(o.hg + i, k) = gt[i];
-        }
-        __syncwarp();
-    }
-
-    // rho_l, rho_u (slack-elimination right-hand sides) and q_lg, q_ug of obstacle j at node k
+    // q_lg, q_ug and the slack-elimination right-hand sides rho_l, rho_u of obstacle j at node k, base kinds
     __device__ __forceinline__ void slack_rho(int kind, double smu, int j, const double* v, double Zuq, double sc,
                                               double& rhol, double& rhou, double& q0, double& q1) const
     {
         const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
-        if (kind == 3) {
-            q0 = q1 = 0.0;
-            rhol = S(o.lrgsl + j, k);
-            rhou = S(o.lrgsu + j, k);
-            return;
-        }
         const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
         const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
         const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
@@ -420,103 +403,159 @@ struct WppSolver {
         const double q3 = (rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * rd3) * S(o.tinv + i3, k);
         const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
         const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
-        // esl/esu: slack right-hand sides added by iterative refinement of this step
-        rhol = rgsl + S(o.esl + j, k) + q0 + q2;
-        rhou = rgsu + S(o.esu + j, k) + q1 + q3;
+        rhol = rgsl + q0 + q2;
+        rhou = rgsu + q1 + q3;
     }
 
-    // backward + forward vector sweeps with the current factorisation (sequential in k);
-    // kind 3 ACCUMULATES the correction into dv/dpi
-    __device__ void riccati_solve(int kind)
+    // node-local part of a solve: condensed gradient of node k for the right-hand side `kind`
+    // (0 affine, 1 corrector, 2 centering, 3 refinement = linear residual) -> rows hg[0..6]
+    __device__ void solve_prep(int kind, double smu)
     {
-        if (lane != 0) return;
-        const bool itr = (kind == 3);
-        const int oRB = itr ? o.lrb : o.rb;
-        double pn[5] = {0, 0, 0, 0, 0};
-        for (int kk = N; kk >= 0; kk--) {
+        if (act) {
+            const double sc = scal(k);
             double gt[7];
+            if (kind == 3) {
 #pragma unroll
-            for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, kk);
-            if (kk < N) {
-                double sv[10], Pn[15], rb[5], y[5], bt[7];
-#pragma unroll
-                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
-#pragma unroll
-                for (int i = 0; i < 15; i++) Pn[i] = S(o.pm + i, kk + 1);
-#pragma unroll
-                for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, kk);
-                b2_symv(Pn, rb, y);
-#pragma unroll
-                for (int i = 0; i < 5; i++) y[i] += pn[i];
-                b2_bat_mul(sv, p.dt, p.dt2h, y, bt);
-#pragma unroll
-                for (int i = 0; i < 7; i++) gt[i] += bt[i];
-                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
-                const double lu0 = gt[0] * l00i;
-                const double lu1 = (gt[1] - l10 * lu0) * l11i;
-                S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1;
-                if (kk > 0) {
-#pragma unroll
-                    for (int i = 0; i < 5; i++) pn[i] = gt[2 + i] - S(o.lxu + 2 * i, kk) * lu0 - S(o.lxu + 2 * i + 1, kk) * lu1;
+                for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, k);          // lin_residuals left lrg here
+    #pragma unroll 1
+            for (int j = 0; j < M; j++) {
+                    const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
+                    const double coef = -G0 * S(o.lrgsl + j, k) * S(o.dli + j, k) + G1 * S(o.lrgsu + j, k) * S(o.dui + j, k);
+                    gt[2] += S(o.cx + j, k) * coef;
+                    gt[3] += S(o.cy + j, k) * coef;
                 }
             } else {
+                double v[7];
 #pragma unroll
-                for (int i = 0; i < 5; i++) pn[i] = gt[2 + i];
-            }
-            if (kk > 0) {
+                for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = S(o.rg + i, k); }
 #pragma unroll
-                for (int i = 0; i < 5; i++) S(o.pv + i, kk) = pn[i];
+                for (int s = 0; s < 6; s++) {
+                    if (!box_on(s, k)) continue;
+                    const int il = o_lb + s, iu = o_ub + s;
+                    const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
+                    const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+                    const double ql = (rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * rdl) * S(o.tinv + il, k);
+                    const double qu = (rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * rdu) * S(o.tinv + iu, k);
+                    gt[b2_slot2v(s)] += ql - qu;
+                }
+                const double Zuq = sc * p.Zu;
+    #pragma unroll 1
+            for (int j = 0; j < M; j++) {
+                    double rhol, rhou, q0, q1;
+                    slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
+                    const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
+                    const double coef = (q0 - G0 * rhol * S(o.dli + j, k)) - (q1 - G1 * rhou * S(o.dui + j, k));
+                    gt[2] += S(o.cx + j, k) * coef;
+                    gt[3] += S(o.cy + j, k) * coef;
+                }
             }
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.hg + i, k) = gt[i];
         }
+        __syncwarp();
+    }
+
+    // backward + forward vector sweeps with the current factorisation; lanes 0..6 own rows/columns.
+    // kind 3 reads the linear residual (lrb) and writes the correction to cv/cpi.
+    __device__ void riccati_solve(int kind)
+    {
+        const bool itr = (kind == 3);
+        const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.dv, oDPI = itr ? o.cpi : o.dpi;
+        const int c7 = lane < 7 ? lane : 6;            // column owned in the backward sweep
+        const int r5 = (lane >= 2 && lane < 7) ? lane - 2 : 0;   // row of y / p owned in the backward sweep (lanes 2..6)
+        const int f5 = lane < 5 ? lane : 4;            // row owned in the forward sweep (lanes 0..4)
+        int colidx[5], rowidx[7], prow_b[5], prow_f[5];
+#pragma unroll
+        for (int r = 0; r < 5; r++) { colidx[r] = o.sv + B2_BATAB[r][c7]; prow_b[r] = o.pm + b2_sym(r5, r); prow_f[r] = o.pm + b2_sym(f5, r); }
+#pragma unroll
+        for (int c = 0; c < 7; c++) rowidx[c] = o.sv + B2_BATAB[f5][c];
+        // ---- backward: p_k, lu_k
+        double pn = 0.0;
+        for (int kk = N; kk >= 0; kk--) {
+            const double gt = S(o.hg + c7, kk);
+            if (kk < N) {
+                double y = pn;
+#pragma unroll
+                for (int q = 0; q < 5; q++) y += S(prow_b[q], kk + 1) * S(oRB + q, kk);
+                double m = gt;
+#pragma unroll
+                for (int r = 0; r < 5; r++) m += S(colidx[r], kk) * b2_bcast(y, 2 + r);
+                const double m0 = b2_bcast(m, 0), m1 = b2_bcast(m, 1);
+                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+                const double lu0 = m0 * l00i;
+                const double lu1 = (m1 - l10 * lu0) * l11i;
+                if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
+                if (kk > 0) pn = m - S(o.lxu + 2 * r5, kk) * lu0 - S(o.lxu + 2 * r5 + 1, kk) * lu1;
+            } else {
+                pn = gt;
+            }
+            if (kk > 0 && lane >= 2 && lane < 7) S(o.pv + r5, kk) = pn;
+        }
+        __syncwarp();
+        // ---- forward: dv_k, dpi_k
         double dx[5] = {0, 0, 0, 0, 0};
         for (int kk = 0; kk <= N; kk++) {
-            double dv[7] = {0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int i = 0; i < 5; i++) dv[2 + i] = dx[i];
+            double du0 = 0.0, du1 = 0.0;
             if (kk < N) {
-                double sv[10];
-#pragma unroll
-                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, kk);
                 const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
                 double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
                 if (kk > 0) {
 #pragma unroll
                     for (int i = 0; i < 5; i++) { r0 += S(o.lxu + 2 * i, kk) * dx[i]; r1 += S(o.lxu + 2 * i + 1, kk) * dx[i]; }
                 }
-                r0 = -r0; r1 = -r1;
-                dv[1] = r1 * l11i;
-                dv[0] = (r0 - l10 * dv[1]) * l00i;
-                double xn[5], Pn[15], dpi[5];
-                b2_ba_mul(sv, p.dt, p.dt2h, dv, xn);
+                du1 = -r1 * l11i;
+                du0 = (-r0 - l10 * du1) * l00i;
+                double xn = S(oRB + f5, kk) + S(rowidx[0], kk) * du0 + S(rowidx[1], kk) * du1;
 #pragma unroll
-                for (int i = 0; i < 5; i++) xn[i] += S(oRB + i, kk);
+                for (int i = 0; i < 5; i++) xn += S(rowidx[2 + i], kk) * dx[i];
+                // store dv_k before dx is overwritten
+                double val = du0;
+                if (lane == 1) val = du1;
 #pragma unroll
-                for (int i = 0; i < 15; i++) Pn[i] = S(o.pm + i, kk + 1);
-                b2_symv(Pn, xn, dpi);
+                for (int i = 0; i < 5; i++) if (lane == 2 + i) val = dx[i];
+                if (lane < 7) S(oDV + lane, kk) = val;
 #pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    dpi[i] += S(o.pv + i, kk + 1);
-                    if (itr) S(o.dpi + i, kk) += dpi[i]; else S(o.dpi + i, kk) = dpi[i];
-                    dx[i] = xn[i];
-                }
+                for (int i = 0; i < 5; i++) dx[i] = b2_bcast(xn, i);
+                double dpi = S(o.pv + f5, kk + 1);
+#pragma unroll
+                for (int q = 0; q < 5; q++) dpi += S(prow_f[q], kk + 1) * dx[q];
+                if (lane < 5) S(oDPI + lane, kk) = dpi;
+            } else {
+                double val = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; i++) if (lane == 2 + i) val = dx[i];
+                if (lane < 7) S(oDV + lane, kk) = val;
             }
-#pragma unroll
-            for (int i = 0; i < 7; i++) { if (itr) S(o.dv + i, kk) += dv[i]; else S(o.dv + i, kk) = dv[i]; }
         }
+        __syncwarp();
     }
 
-    // node-local expansion of the (total) step of node k: ds, dt, dlam of every constraint, consumed
-    // on the fly.  MODE XP_ALPHA: step-length / mu_aff reductions (+ store dt*dlam for kind 0);
-    // XP_UPDATE: apply the step with length a; XP_LIN: assemble the linear-system residual.
+    // node-local expansion of node k: slack steps, dt, dlam for every constraint, consumed on the fly.
+    //  XP_SOLVE : base solve `kind` from dv: store dlam (kind 0 with predictor-corrector: store dt*dlam
+    //             in the same slot instead, the corrector consumes it), store dsl/dsu, reduce alpha/S1/S2
+    //  XP_REFINE: add the correction (cv,cpi) of one refinement step: dlam += -lam*dt_c/t, dsl/dsu += ...,
+    //             dv += cv, dpi += cpi; reduce alpha/S1/S2 on the totals
+    //  XP_UPDATE: apply the stored step with length a
+    //  XP_LIN   : assemble the residual of the linear system at the stored step
     template <int MODE>
     __device__ __forceinline__ void expand(int kind, double smu, double a, double& ap, double& ad, double& s1, double& s2,
                                            double* lrg, double& ln0)
     {
         const double sc = scal(k);
         const double Zuq = sc * p.Zu;
-        double v[7], dv[7];
+        const bool keep_dd = (MODE == XP_SOLVE) && kind == 0 && p.pred_corr;
+        double v[7], dv[7], cv[7];
 #pragma unroll
-        for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); dv[i] = S(o.dv + i, k); }
+        for (int i = 0; i < 7; i++) {
+            v[i] = S(o.v + i, k);
+            dv[i] = S(o.dv + i, k);
+            cv[i] = 0.0;
+            if (MODE == XP_REFINE) { cv[i] = S(o.cv + i, k); dv[i] += cv[i]; S(o.dv + i, k) = dv[i]; }
+        }
+        if (MODE == XP_REFINE && k < N) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) S(o.dpi + i, k) += S(o.cpi + i, k);
+        }
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             if (!box_on(s, k)) continue;
@@ -525,43 +564,76 @@ struct WppSolver {
             const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
             const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
             const double dtl = dv[iv] + rdl, dtu = -dv[iv] + rdu;
-            const double dll = -(rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * dtl) * S(o.tinv + il, k);
-            const double dlu = -(rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * dtu) * S(o.tinv + iu, k);
-            consume<MODE>(kind, il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
-            consume<MODE>(kind, iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
+            double dll, dlu;
+            if (MODE == XP_SOLVE) {
+                dll = -(rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * dtl) * S(o.tinv + il, k);
+                dlu = -(rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * dtu) * S(o.tinv + iu, k);
+                S(o.dd + il, k) = keep_dd ? dtl * dll : dll;
+                S(o.dd + iu, k) = keep_dd ? dtu * dlu : dlu;
+            } else if (MODE == XP_REFINE) {
+                dll = S(o.dd + il, k) - ll * cv[iv] * S(o.tinv + il, k);
+                dlu = S(o.dd + iu, k) + lu_ * cv[iv] * S(o.tinv + iu, k);
+                S(o.dd + il, k) = dll; S(o.dd + iu, k) = dlu;
+            } else {
+                dll = S(o.dd + il, k); dlu = S(o.dd + iu, k);
+            }
+            consume<MODE>(il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
+            consume<MODE>(iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
             if (MODE == XP_LIN) lrg[iv] += -dll + dlu;
         }
+#pragma unroll 1
         for (int j = 0; j < M; j++) {
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
-            double rhol, rhou, q0, q1;
-            slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
             const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
             const double cdv = cx * dv[2] + cy * dv[3];
             const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
             const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
-            const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
-            const double dsl = -(l0 * ti0 * cdv + rhol) * S(o.dli + j, k);
-            const double dsu = -(-l1 * ti1 * cdv + rhou) * S(o.dui + j, k);
             const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
-            const double cv = cx * v[2] + cy * v[3];
-            const double rd0 = cv + s_l - S(o.lg + j, k) - t0;
-            const double rd1 = S(o.ug + j, k) - cv + s_u - t1;
+            const double cval = cx * v[2] + cy * v[3];
+            const double rd0 = cval + s_l - S(o.lg + j, k) - t0;
+            const double rd1 = S(o.ug + j, k) - cval + s_u - t1;
             const double rd2 = s_l + S(o.sli + j, k) - t2;
             const double rd3 = s_u + S(o.sui + j, k) - t3;
+            double dsl, dsu, dl0, dl1, dl2, dl3;
+            if (MODE == XP_SOLVE) {
+                const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
+                double rhol, rhou, q0, q1;
+                slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
+                dsl = -(l0 * ti0 * cdv + rhol) * S(o.dli + j, k);
+                dsu = -(-l1 * ti1 * cdv + rhou) * S(o.dui + j, k);
+                S(o.dsl + j, k) = dsl; S(o.dsu + j, k) = dsu;
+                const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
+                dl0 = -(rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * dt0) * ti0;
+                dl1 = -(rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * dt1) * ti1;
+                dl2 = -(rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * dt2) * ti2;
+                dl3 = -(rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * dt3) * ti3;
+                S(o.dd + i0, k) = keep_dd ? dt0 * dl0 : dl0; S(o.dd + i1, k) = keep_dd ? dt1 * dl1 : dl1;
+                S(o.dd + i2, k) = keep_dd ? dt2 * dl2 : dl2; S(o.dd + i3, k) = keep_dd ? dt3 * dl3 : dl3;
+            } else if (MODE == XP_REFINE) {
+                const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
+                const double ccv = cx * cv[2] + cy * cv[3];
+                const double csl = -(l0 * ti0 * ccv + S(o.lrgsl + j, k)) * S(o.dli + j, k);
+                const double csu = -(-l1 * ti1 * ccv + S(o.lrgsu + j, k)) * S(o.dui + j, k);
+                dsl = S(o.dsl + j, k) + csl; dsu = S(o.dsu + j, k) + csu;
+                S(o.dsl + j, k) = dsl; S(o.dsu + j, k) = dsu;
+                dl0 = S(o.dd + i0, k) - l0 * (ccv + csl) * ti0;
+                dl1 = S(o.dd + i1, k) - l1 * (-ccv + csu) * ti1;
+                dl2 = S(o.dd + i2, k) - l2 * csl * ti2;
+                dl3 = S(o.dd + i3, k) - l3 * csu * ti3;
+                S(o.dd + i0, k) = dl0; S(o.dd + i1, k) = dl1; S(o.dd + i2, k) = dl2; S(o.dd + i3, k) = dl3;
+            } else {
+                dsl = S(o.dsl + j, k); dsu = S(o.dsu + j, k);
+                dl0 = S(o.dd + i0, k); dl1 = S(o.dd + i1, k); dl2 = S(o.dd + i2, k); dl3 = S(o.dd + i3, k);
+            }
             const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
-            const double dl0 = -(rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * dt0) * ti0;
-            const double dl1 = -(rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * dt1) * ti1;
-            const double dl2 = -(rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * dt2) * ti2;
-            const double dl3 = -(rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * dt3) * ti3;
-            consume<MODE>(kind, i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
-            consume<MODE>(kind, i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
-            consume<MODE>(kind, i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
-            consume<MODE>(kind, i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
+            consume<MODE>(i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
+            consume<MODE>(i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
+            consume<MODE>(i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
+            consume<MODE>(i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
             if (MODE == XP_UPDATE) { S(o.sl + j, k) = s_l + a * dsl; S(o.su + j, k) = s_u + a * dsu; }
             if (MODE == XP_LIN) {
                 const double dl = dl1 - dl0;
                 lrg[2] += cx * dl; lrg[3] += cy * dl;
-                // slack rows of the linear system: Z ds + (rgs + es) - dlam_g - dlam_s
                 const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
                 const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
                 const double a0 = S(o.Zlq + j, k) * dsl + rgsl - dl0 - dl2;
@@ -572,14 +644,18 @@ struct WppSolver {
         }
     }
 
+    // running "most limiting" ratios lam/dlam and t/dt (HPIPM d_compute_alpha_qp, negative-reciprocal
+    // convention) kept as numerator/denominator pairs: one division per lane at the end
+    double ad_n, ad_d, ap_n, ap_d;
+
     template <int MODE>
-    __device__ __forceinline__ void consume(int kind, int i, double l, double t, double dti, double dli, double a,
+    __device__ __forceinline__ void consume(int i, double l, double t, double dti, double dli, double a,
                                             double& ap, double& ad, double& s1, double& s2)
     {
-        if (MODE == XP_ALPHA) {
-            if (kind == 0) S(o.dd + i, k) = dti * dli;
-            if (ad * dli > l) ad = l / dli;
-            if (ap * dti > t) ap = t / dti;
+        if (MODE == XP_SOLVE || MODE == XP_REFINE) {
+            // (ad_n/ad_d) * dli > l  with ad_d < 0   <=>   ad_n * dli < l * ad_d
+            if (ad_n * dli < l * ad_d) { ad_n = l; ad_d = dli; }
+            if (ap_n * dti < t * ap_d) { ap_n = t; ap_d = dti; }
             s1 += l * dti + t * dli;
             s2 += dli * dti;
         } else if (MODE == XP_UPDATE) {
@@ -590,43 +666,42 @@ struct WppSolver {
         }
     }
 
-    // solve for a base right-hand side (kind 0 affine, 1 corrector, 2 centering) + step-length reductions
-    __device__ void solve_base(int kind, double smu)
+    __device__ void reduce_step_length(double ap, double ad, double s1, double s2)
     {
-        if (act) {
-            for (int j = 0; j < M; j++) { S(o.esl + j, k) = 0.0; S(o.esu + j, k) = 0.0; }
-        }
-        solve_prep(kind, smu);
-        riccati_solve(kind);
-        __syncwarp();
-        step_length(kind, smu);
-    }
-
-    // one iterative-refinement step on the current direction: solve for the linear residual, accumulate
-    __device__ void solve_refine(int base_kind, double smu)
-    {
-        solve_prep(3, 0.0);
-        riccati_solve(3);
-        __syncwarp();
-        if (act) {
-            for (int j = 0; j < M; j++) { S(o.esl + j, k) += S(o.lrgsl + j, k); S(o.esu + j, k) += S(o.lrgsu + j, k); }
-        }
-        __syncwarp();
-        step_length(base_kind, smu);
-    }
-
-    __device__ void step_length(int kind, double smu)
-    {
-        double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
-        if (act) expand<XP_ALPHA>(kind, smu, 0.0, ap, ad, s1, s2, nullptr, dummy);
-        // max of the negative reciprocals == min of the admissible step lengths (HPIPM convention)
+        // max of the negative reciprocals == min of the admissible step lengths
         ap = b2_warp_max(ap); ad = b2_warp_max(ad);
         S1 = b2_warp_sum(s1); S2 = b2_warp_sum(s2);
         alpha = -(ap > ad ? ap : ad);
+    }
+
+    // solve for a base right-hand side (0 affine, 1 corrector, 2 centering) + step-length reductions
+    __device__ void solve_base(int kind, double smu)
+    {
+        solve_prep(kind, smu);
+        riccati_solve(kind);
+        double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
+        ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
+        if (act) expand<XP_SOLVE>(kind, smu, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        ap = ap_n / ap_d; ad = ad_n / ad_d;
+        reduce_step_length(ap, ad, s1, s2);
         __syncwarp();
     }
 
-    __device__ void lin_residuals(int kind, double smu, double lnrm[2])
+    // one iterative-refinement step: solve for the linear residual and add the correction
+    __device__ void solve_refine()
+    {
+        solve_prep(3, 0.0);
+        riccati_solve(3);
+        double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
+        ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
+        if (act) expand<XP_REFINE>(3, 0.0, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        ap = ap_n / ap_d; ad = ad_n / ad_d;
+        reduce_step_length(ap, ad, s1, s2);
+        __syncwarp();
+    }
+
+    // residual of the linear system at the stored step; leaves lrg in rows hg[0..6] for solve_prep(3)
+    __device__ void lin_residuals(double lnrm[2])
     {
         double ln0 = 0.0, ln1 = 0.0;
         if (act) {
@@ -650,7 +725,7 @@ struct WppSolver {
                 for (int i = 0; i < 5; i++) lrg[2 + i] -= S(o.dpi + i, k - 1);
             }
             double ap = 0, ad = 0, s1 = 0, s2 = 0;
-            expand<XP_LIN>(kind, smu, 0.0, ap, ad, s1, s2, lrg, ln0);
+            expand<XP_LIN>(0, 0.0, 0.0, ap, ad, s1, s2, lrg, ln0);
             if (k < N) {
                 double lrb[5];
                 b2_ba_mul(sv, p.dt, p.dt2h, dv, lrb);
@@ -664,17 +739,17 @@ struct WppSolver {
             if (k == 0) { lrg[2] = lrg[3] = lrg[4] = lrg[5] = lrg[6] = 0.0; }
             if (k == N) { lrg[0] = lrg[1] = 0.0; }
 #pragma unroll
-            for (int i = 0; i < 7; i++) { S(o.lrg + i, k) = lrg[i]; ln0 = fmax(ln0, fabs(lrg[i])); }
+            for (int i = 0; i < 7; i++) { S(o.hg + i, k) = lrg[i]; ln0 = fmax(ln0, fabs(lrg[i])); }
         }
         lnrm[0] = b2_warp_max(ln0); lnrm[1] = b2_warp_max(ln1);
         __syncwarp();
     }
 
-    __device__ void update(int kind, double smu, double a)
+    __device__ void update(double a)
     {
         if (act) {
             double ap = 0, ad = 0, s1 = 0, s2 = 0, dummy = 0;
-            expand<XP_UPDATE>(kind, smu, a, ap, ad, s1, s2, nullptr, dummy);
+            expand<XP_UPDATE>(0, 0.0, a, ap, ad, s1, s2, nullptr, dummy);
 #pragma unroll
             for (int i = 0; i < 7; i++) S(o.v + i, k) += a * S(o.dv + i, k);
             if (k < N) {
@@ -696,31 +771,29 @@ struct WppSolver {
         for (; kk < p.qp_iter_max && alpha > p.alpha_min &&
                (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max); kk++) {
             factorize();
-            int base = 0;
-            double smu = 0.0;
             solve_base(0, 0.0);
             if (p.pred_corr) {
                 double mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
                 const double tmp = mu_aff / mu;
-                smu = tmp * tmp * tmp * mu;
+                double smu = tmp * tmp * tmp * mu;
                 smu = smu > p.tau_min ? smu : p.tau_min;
-                solve_base(1, smu); base = 1;
+                solve_base(1, smu);
                 if (p.cond_pred_corr) {
                     const double mu_aff0 = mu_aff;
                     mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
-                    if (mu_aff > 2.0 * mu_aff0) { solve_base(2, smu); base = 2; }
+                    if (mu_aff > 2.0 * mu_aff0) solve_base(2, smu);
                 }
                 for (int it = 0; it < p.itref_corr_max; it++) {
                     double lnrm[2];
-                    lin_residuals(base, smu, lnrm);
+                    lin_residuals(lnrm);
                     if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
-                    solve_refine(base, smu);
+                    solve_refine();
                     n_itref++;
                 }
             }
             double a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-            update(base, smu, a);
+            update(a);
             residuals();
         }
         int qs;
@@ -737,7 +810,8 @@ struct WppSolver {
                     p.U[((size_t)k * 2 + 0) * Bm + b] += S(o.v + 0, k);
                     p.U[((size_t)k * 2 + 1) * Bm + b] += S(o.v + 1, k);
                 }
-                for (int j = 0; j < M; j++) {
+    #pragma unroll 1
+            for (int j = 0; j < M; j++) {
                     p.SL[((size_t)k * M + j) * Bm + b] += S(o.sl + j, k);
                     p.SU[((size_t)k * M + j) * Bm + b] += S(o.su + j, k);
                 }
@@ -760,12 +834,12 @@ struct WppSolver {
     }
 };
 
-template <int MT>
+template <int MT, int NT>
 __global__ void __launch_bounds__(32) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        WppSolver<MT> s(p, b, b2_smem);
+        WppSolver<MT, NT> s(p, b, b2_smem);
         s.run();
     }
 }
