@@ -30,7 +30,7 @@ __constant__ unsigned char B2_BATAB[5][7] = {
 };
 
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, pm, pv, lu;               // used by the sweeps
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, minv, kmat, pm, pv;                  // used by the sweeps
     int lam, t, tinv, dd;                                                       // per constraint (nct rows each); dd doubles as dlam
     int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrgsl, lrgsu, dsl, dsu, dli, dui, xu;
     int total;
@@ -39,7 +39,7 @@ struct WOff {
         const int nct = 12 + 4 * M;
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
-        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; pm = o; o += 15; pv = o; o += 5; lu = o; o += 2;
+        cv = o; o += 7; cpi = o; o += 5; minv = o; o += 3; kmat = o; o += 10; pm = o; o += 15; pv = o; o += 5;
         lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
         b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
         zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
@@ -332,7 +332,7 @@ struct WppSolver {
         const bool xx = lane < 28 && mi >= 2 && mj >= 2;
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
         const int prow = xx ? o.pm + b2_sym(mi - 2, mj - 2) : 0;
-        const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
+        const int krow = xu ? o.kmat + 5 * mj + (mi - 2) : 0;
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
             if (mi == mj) m = S(o.hg + mi, kk);
@@ -355,20 +355,18 @@ struct WppSolver {
                 for (int r = 0; r < 5; r++) acc += a[r] * w[r];
                 m += acc;
                 const double m00 = b2_bcast(m, 0), m10 = b2_bcast(m, 1), m11 = b2_bcast(m, 2);
-                const double l00 = m00 > 0.0 ? sqrt(m00) : 0.0;
-                const double l00i = l00 > 0.0 ? 1.0 / l00 : 0.0;
-                const double l10 = m10 * l00i;
-                const double d11 = m11 - l10 * l10;
-                const double l11 = d11 > 0.0 ? sqrt(d11) : 0.0;
-                const double l11i = l11 > 0.0 ? 1.0 / l11 : 0.0;
+                // inverse of the 2x2 control block (positive definite: Hd + LM > 0)
+                const double det = m00 * m11 - m10 * m10;
+                const double di = (det > 0.0 && m00 > 0.0) ? 1.0 / det : 0.0;
+                const double i00 = m11 * di, i01 = -m10 * di, i11 = m00 * di;
                 const double mi0 = b2_bcast(m, src_i0), mi1 = b2_bcast(m, src_i1);
                 const double mj0 = b2_bcast(m, src_j0), mj1 = b2_bcast(m, src_j1);
-                const double Li0 = mi0 * l00i, Li1 = (mi1 - Li0 * l10) * l11i;
-                const double Lj0 = mj0 * l00i, Lj1 = (mj1 - Lj0 * l10) * l11i;
-                if (lane == 0) { S(o.lamu + 0, kk) = l00i; S(o.lamu + 1, kk) = l10; S(o.lamu + 2, kk) = l11i; }
+                // feedback gain K = -Muu^-1 Mux (column of node state mj-2 / mi-2)
+                const double Kj0 = -(i00 * mj0 + i01 * mj1), Kj1 = -(i01 * mj0 + i11 * mj1);
+                if (lane == 0) { S(o.minv + 0, kk) = i00; S(o.minv + 1, kk) = i01; S(o.minv + 2, kk) = i11; }
                 if (kk > 0) {
-                    if (xx) S(prow, kk) = m - Li0 * Lj0 - Li1 * Lj1;
-                    if (xu) S(lrow, kk) = (mj == 0) ? Li0 : Li1;
+                    if (xx) S(prow, kk) = m + mi0 * Kj0 + mi1 * Kj1;           // P = Mxx + Mxu K
+                    if (xu) S(krow, kk) = (mj == 0) ? -(i00 * mi0 + i01 * mi1) : -(i01 * mi0 + i11 * mi1);
                 }
             } else {
                 if (xx) S(prow, kk) = m;
@@ -455,76 +453,94 @@ struct WppSolver {
         __syncwarp();
     }
 
-    // backward + forward vector sweeps with the current factorisation; lanes 0..6 own rows/columns.
+    // backward + forward vector sweeps with the current factorisation.  Everything that does not
+    // depend on the recursion (z_k = P+ rb_k before, dpi_k = P+ dx+ + p+ after) is node-parallel; the
+    // sequential cores are  p_k = gx + A^T s + K^T w,  w = gu + B^T s,  s = p+ + z   (lanes 0..4 own the
+    // components, w is computed redundantly) and  dx+ = A dx + B du + rb,  du = K dx + kff.
     // kind 3 reads the linear residual (lrb) and writes the correction to cv/cpi.
     __device__ void riccati_solve(int kind)
     {
         const bool itr = (kind == 3);
         const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.dv, oDPI = itr ? o.cpi : o.dpi;
-        const int c7 = lane < 7 ? lane : 6;            // column owned in the backward sweep
-        const int r5 = (lane >= 2 && lane < 7) ? lane - 2 : 0;   // row of y / p owned in the backward sweep (lanes 2..6)
-        const int f5 = lane < 5 ? lane : 4;            // row owned in the forward sweep (lanes 0..4)
-        int colidx[5], rowidx[7], prow_b[5], prow_f[5];
+        if (act && k < N) {
+            double P[15], rb[5];
 #pragma unroll
-        for (int r = 0; r < 5; r++) { colidx[r] = o.sv + B2_BATAB[r][c7]; prow_b[r] = o.pm + b2_sym(r5, r); prow_f[r] = o.pm + b2_sym(f5, r); }
+            for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, k + 1);
 #pragma unroll
-        for (int c = 0; c < 7; c++) rowidx[c] = o.sv + B2_BATAB[f5][c];
-        // ---- backward: p_k, lu_k
-        double pn = 0.0;
-        for (int kk = N; kk >= 0; kk--) {
-            const double gt = S(o.hg + c7, kk);
-            if (kk < N) {
-                double y = pn;
+            for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
 #pragma unroll
-                for (int q = 0; q < 5; q++) y += S(prow_b[q], kk + 1) * S(oRB + q, kk);
-                double m = gt;
+            for (int i = 0; i < 5; i++) {
+                double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < 5; r++) m += S(colidx[r], kk) * b2_bcast(y, 2 + r);
-                const double m0 = b2_bcast(m, 0), m1 = b2_bcast(m, 1);
-                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
-                const double lu0 = m0 * l00i;
-                const double lu1 = (m1 - l10 * lu0) * l11i;
-                if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
-                if (kk > 0) pn = m - S(o.lxu + 2 * r5, kk) * lu0 - S(o.lxu + 2 * r5 + 1, kk) * lu1;
-            } else {
-                pn = gt;
+                for (int q = 0; q < 5; q++) acc += P[b2_sym(i, q)] * rb[q];
+                S(oDPI + i, k) = acc;                                   // z_k (overwritten by dpi_k below)
             }
-            if (kk > 0 && lane >= 2 && lane < 7) S(o.pv + r5, kk) = pn;
         }
         __syncwarp();
-        // ---- forward: dv_k, dpi_k
+        const int c5 = lane < 5 ? lane : 4;
+        int acol[5], arow[7];
+#pragma unroll
+        for (int r = 0; r < 5; r++) acol[r] = o.sv + B2_BATAB[r][2 + c5];
+#pragma unroll
+        for (int c = 0; c < 7; c++) arow[c] = o.sv + B2_BATAB[c5][c];
+        const double h = p.dt, h2 = p.dt2h;
+        // ---- backward
+        double pf[5];
+        {
+            const double pc = S(o.hg + 2 + c5, N);
+            if (lane < 5) S(o.pv + lane, N) = pc;
+#pragma unroll
+            for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
+        }
+        for (int kk = N - 1; kk >= 0; kk--) {
+            double s[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) s[r] = pf[r] + S(oDPI + r, kk);
+            const double w0 = S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0] + S(o.sv + SV_B10, kk) * s[1] + h * s[3];
+            const double w1 = S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0] + S(o.sv + SV_B11, kk) * s[1] + h2 * s[2] + h * s[4];
+            const double i00 = S(o.minv + 0, kk), i01 = S(o.minv + 1, kk), i11 = S(o.minv + 2, kk);
+            if (lane == 0) { S(oDV + 0, kk) = -(i00 * w0 + i01 * w1); S(oDV + 1, kk) = -(i01 * w0 + i11 * w1); }   // kff
+            if (kk > 0) {
+                double pc = S(o.hg + 2 + c5, kk) + S(o.kmat + c5, kk) * w0 + S(o.kmat + 5 + c5, kk) * w1;
+#pragma unroll
+                for (int r = 0; r < 5; r++) pc += S(acol[r], kk) * s[r];
+                if (lane < 5) S(o.pv + lane, kk) = pc;
+#pragma unroll
+                for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
+            }
+        }
+        __syncwarp();
+        // ---- forward
         double dx[5] = {0, 0, 0, 0, 0};
-        for (int kk = 0; kk <= N; kk++) {
-            double du0 = 0.0, du1 = 0.0;
-            if (kk < N) {
-                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
-                double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
-                if (kk > 0) {
+        if (lane < 5) S(oDV + 2 + lane, 0) = 0.0;
+        for (int kk = 0; kk < N; kk++) {
+            double du0 = S(oDV + 0, kk), du1 = S(oDV + 1, kk);
+            if (kk > 0) {
 #pragma unroll
-                    for (int i = 0; i < 5; i++) { r0 += S(o.lxu + 2 * i, kk) * dx[i]; r1 += S(o.lxu + 2 * i + 1, kk) * dx[i]; }
-                }
-                du1 = -r1 * l11i;
-                du0 = (-r0 - l10 * du1) * l00i;
-                double xn = S(oRB + f5, kk) + S(rowidx[0], kk) * du0 + S(rowidx[1], kk) * du1;
+                for (int c = 0; c < 5; c++) { du0 += S(o.kmat + c, kk) * dx[c]; du1 += S(o.kmat + 5 + c, kk) * dx[c]; }
+            }
+            double xn = S(oRB + c5, kk) + S(arow[0], kk) * du0 + S(arow[1], kk) * du1;
 #pragma unroll
-                for (int i = 0; i < 5; i++) xn += S(rowidx[2 + i], kk) * dx[i];
-                // store dv_k before dx is overwritten
-                double val = du0;
-                if (lane == 1) val = du1;
+            for (int c = 0; c < 5; c++) xn += S(arow[2 + c], kk) * dx[c];
+            if (lane == 0) { S(oDV + 0, kk) = du0; S(oDV + 1, kk) = du1; }
+            if (lane < 5) S(oDV + 2 + lane, kk + 1) = xn;
 #pragma unroll
-                for (int i = 0; i < 5; i++) if (lane == 2 + i) val = dx[i];
-                if (lane < 7) S(oDV + lane, kk) = val;
+            for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
+        }
+        if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
+        __syncwarp();
+        if (act && k < N) {
+            double P[15], dxn[5];
 #pragma unroll
-                for (int i = 0; i < 5; i++) dx[i] = b2_bcast(xn, i);
-                double dpi = S(o.pv + f5, kk + 1);
+            for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, k + 1);
 #pragma unroll
-                for (int q = 0; q < 5; q++) dpi += S(prow_f[q], kk + 1) * dx[q];
-                if (lane < 5) S(oDPI + lane, kk) = dpi;
-            } else {
-                double val = 0.0;
+            for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
 #pragma unroll
-                for (int i = 0; i < 5; i++) if (lane == 2 + i) val = dx[i];
-                if (lane < 7) S(oDV + lane, kk) = val;
+            for (int i = 0; i < 5; i++) {
+                double acc = S(o.pv + i, k + 1);
+#pragma unroll
+                for (int q = 0; q < 5; q++) acc += P[b2_sym(i, q)] * dxn[q];
+                S(oDPI + i, k) = acc;
             }
         }
         __syncwarp();
