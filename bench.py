@@ -278,7 +278,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": int(tot_B), "l2": "flushed between steps (256 MiB memset)",
-                       "kernel": "thread-per-problem" if a.kernel in (0, 1) else "warp-per-problem",
+                       "kernel": solver.kernel_name,
                        "parallelism": f"env-sharded x{world_size}, no data-path collective"},
             "p50_latency_ms_per_batch": float(np.median(step_ms)),
             "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),

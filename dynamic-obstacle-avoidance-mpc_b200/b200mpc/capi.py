@@ -43,7 +43,7 @@ EXPORTS = [
     "b2mpc_field_len", "b2mpc_workspace_bytes", "b2mpc_set", "b2mpc_get", "b2mpc_get_i32",
     "b2mpc_set_host", "b2mpc_get_host", "b2mpc_get_i32_host", "b2mpc_field_ptr",
     "b2mpc_prepare_slack", "b2mpc_reset", "b2mpc_solve", "b2mpc_sim", "b2mpc_shift",
-    "b2mpc_launch_count", "b2mpc_solve_host", "b2mpc_dfma_peak",
+    "b2mpc_launch_count", "b2mpc_kernel", "b2mpc_solve_host", "b2mpc_dfma_peak",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.b2mpc_field_len.argtypes = [vp, C.c_int]; L.b2mpc_field_len.restype = i64
     L.b2mpc_workspace_bytes.argtypes = [vp]; L.b2mpc_workspace_bytes.restype = i64
     L.b2mpc_launch_count.argtypes = [vp]; L.b2mpc_launch_count.restype = i64
+    L.b2mpc_kernel.argtypes = [vp]
     L.b2mpc_field_ptr.argtypes = [vp, C.c_int]; L.b2mpc_field_ptr.restype = vp
     for name in ("b2mpc_set", "b2mpc_get"):
         getattr(L, name).argtypes = [vp, C.c_int, vp, i64, C.c_int, vp]

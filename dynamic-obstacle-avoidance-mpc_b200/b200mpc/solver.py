@@ -133,6 +133,10 @@ class BatchedMpcSolver:
         return status, qp_iter
 
     @property
+    def kernel_name(self):
+        return {1: "thread-per-problem", 2: "warp-per-problem"}[capi.lib().b2mpc_kernel(self._h)]
+
+    @property
     def launch_count(self):
         return capi.lib().b2mpc_launch_count(self._h)
 

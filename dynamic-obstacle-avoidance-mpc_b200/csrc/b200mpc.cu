@@ -195,6 +195,7 @@ extern "C" int64_t b2mpc_field_len(const b2mpc* h, int field)
 }
 extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)h->ws_bytes : -1; }
 extern "C" int64_t b2mpc_launch_count(const b2mpc* h) { return h ? h->launches : -1; }
+extern "C" int b2mpc_kernel(const b2mpc* h) { return h ? h->kernel : -1; }
 extern "C" double* b2mpc_field_ptr(b2mpc* h, int field)
 {
     if (!h || field < 0 || field >= B2MPC_N_FIELDS) return nullptr;

@@ -496,14 +496,16 @@ struct WppSolver {
             double s[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) s[r] = pf[r] + S(oDPI + r, kk);
-            const double w0 = S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0] + S(o.sv + SV_B10, kk) * s[1] + h * s[3];
-            const double w1 = S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0] + S(o.sv + SV_B11, kk) * s[1] + h2 * s[2] + h * s[4];
+            // short dependency trees: the chain through this loop is the critical path of a solve
+            const double w0 = (S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0]) + (S(o.sv + SV_B10, kk) * s[1] + h * s[3]);
+            const double w1 = (S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0]) + (S(o.sv + SV_B11, kk) * s[1] + h2 * s[2]) + h * s[4];
             const double i00 = S(o.minv + 0, kk), i01 = S(o.minv + 1, kk), i11 = S(o.minv + 2, kk);
-            if (lane == 0) { S(oDV + 0, kk) = -(i00 * w0 + i01 * w1); S(oDV + 1, kk) = -(i01 * w0 + i11 * w1); }   // kff
+            const double kff0 = -(i00 * w0 + i01 * w1), kff1 = -(i01 * w0 + i11 * w1);
+            if (lane == 0) { S(oDV + 0, kk) = kff0; S(oDV + 1, kk) = kff1; }
             if (kk > 0) {
-                double pc = S(o.hg + 2 + c5, kk) + S(o.kmat + c5, kk) * w0 + S(o.kmat + 5 + c5, kk) * w1;
-#pragma unroll
-                for (int r = 0; r < 5; r++) pc += S(acol[r], kk) * s[r];
+                const double pa = (S(o.hg + 2 + c5, kk) + S(acol[0], kk) * s[0]) + (S(acol[1], kk) * s[1] + S(acol[2], kk) * s[2]);
+                const double pb = S(acol[3], kk) * s[3] + S(acol[4], kk) * s[4];
+                const double pc = (pa + pb) + (S(o.kmat + c5, kk) * w0 + S(o.kmat + 5 + c5, kk) * w1);
                 if (lane < 5) S(o.pv + lane, kk) = pc;
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
@@ -516,12 +518,11 @@ struct WppSolver {
         for (int kk = 0; kk < N; kk++) {
             double du0 = S(oDV + 0, kk), du1 = S(oDV + 1, kk);
             if (kk > 0) {
-#pragma unroll
-                for (int c = 0; c < 5; c++) { du0 += S(o.kmat + c, kk) * dx[c]; du1 += S(o.kmat + 5 + c, kk) * dx[c]; }
+                du0 = (du0 + S(o.kmat + 0, kk) * dx[0] + S(o.kmat + 1, kk) * dx[1]) + (S(o.kmat + 2, kk) * dx[2] + S(o.kmat + 3, kk) * dx[3] + S(o.kmat + 4, kk) * dx[4]);
+                du1 = (du1 + S(o.kmat + 5, kk) * dx[0] + S(o.kmat + 6, kk) * dx[1]) + (S(o.kmat + 7, kk) * dx[2] + S(o.kmat + 8, kk) * dx[3] + S(o.kmat + 9, kk) * dx[4]);
             }
-            double xn = S(oRB + c5, kk) + S(arow[0], kk) * du0 + S(arow[1], kk) * du1;
-#pragma unroll
-            for (int c = 0; c < 5; c++) xn += S(arow[2 + c], kk) * dx[c];
+            const double xa = (S(oRB + c5, kk) + S(arow[2], kk) * dx[0] + S(arow[3], kk) * dx[1]) + (S(arow[4], kk) * dx[2] + S(arow[5], kk) * dx[3] + S(arow[6], kk) * dx[4]);
+            const double xn = xa + (S(arow[0], kk) * du0 + S(arow[1], kk) * du1);
             if (lane == 0) { S(oDV + 0, kk) = du0; S(oDV + 1, kk) = du1; }
             if (lane < 5) S(oDV + 2 + lane, kk + 1) = xn;
 #pragma unroll

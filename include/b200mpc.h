@@ -123,6 +123,8 @@ int b2mpc_solve(b2mpc *h, int64_t batch, void *stream);
 int b2mpc_sim(b2mpc *h, int64_t batch, void *stream);
 /* warm-start shift, :253-258 */
 int b2mpc_shift(b2mpc *h, int64_t batch, void *stream);
+/* which solve kernel the handle resolved to: 1 = thread-per-problem (generic), 2 = warp-per-problem */
+int b2mpc_kernel(const b2mpc *h);
 /* number of kernels launched by this handle so far (for bench accounting) */
 int64_t b2mpc_launch_count(const b2mpc *h);
 
