@@ -12,8 +12,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
-    return [os.path.join(SRC, f) for f in sorted(os.listdir(SRC)) if f.endswith((".cu", ".cuh"))] + \
+    return [os.path.join(SRC, f) for f in sorted(os.listdir(SRC)) if f.endswith((".cu", ".cuh")) and f != "model_host.cu"] + \
            [os.path.join(os.path.dirname(PKG), "include", "b200mpc.h")]
+
+
+MODEL_HOST_OUT = os.path.join(PKG, "lib", "libb200model_host.so")
+
+
+def build_model_host(force=False):
+    """host build of the generated model functions (CPU tests of the generated code)"""
+    src = os.path.join(SRC, "model_host.cu")
+    deps = [src, os.path.join(SRC, "model_generated.cuh")]
+    os.makedirs(os.path.dirname(MODEL_HOST_OUT), exist_ok=True)
+    stale = (not os.path.exists(MODEL_HOST_OUT)) or any(os.path.getmtime(s) > os.path.getmtime(MODEL_HOST_OUT) for s in deps)
+    if force or stale:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", MODEL_HOST_OUT, src])
+    return MODEL_HOST_OUT
 
 
 def build(force=False, verbose=False):

@@ -10,11 +10,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200mpc.so")
 
 # field ids (include/b200mpc.h)
-X0, P, YREF, ZL, ZZL, X, U, SL, SU, PI, LAM, T, STATS, GOAL, OBST = range(15)
-STATUS, QP_ITER, QP_STATUS = range(3)
+X0, P, YREF, ZL, ZZL, X, U, SL, SU, PI, LAM, T, STATS, GOAL, OBST, MARGIN, U0 = range(17)
+STATUS, QP_ITER, QP_STATUS, STEPS, DONE, OOB, NFAIL = range(7)
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 FIELD_NAMES = {"x0": X0, "p": P, "yref": YREF, "zl": ZL, "Zl": ZZL, "x": X, "u": U, "sl": SL, "su": SU,
-               "pi": PI, "lam": LAM, "t": T, "stats": STATS, "goal": GOAL, "obst": OBST}
+               "pi": PI, "lam": LAM, "t": T, "stats": STATS, "goal": GOAL, "obst": OBST, "margin": MARGIN, "u0": U0}
+IFIELD_NAMES = {"status": STATUS, "qp_iter": QP_ITER, "qp_status": QP_STATUS, "steps": STEPS, "done": DONE, "oob": OOB, "nfail": NFAIL}
 
 
 class Config(C.Structure):
@@ -44,6 +45,7 @@ EXPORTS = [
     "b2mpc_set_host", "b2mpc_get_host", "b2mpc_get_i32_host", "b2mpc_field_ptr",
     "b2mpc_prepare_slack", "b2mpc_reset", "b2mpc_solve", "b2mpc_sim", "b2mpc_shift",
     "b2mpc_launch_count", "b2mpc_kernel", "b2mpc_solve_host", "b2mpc_dfma_peak",
+    "b2mpc_obst_predict", "b2mpc_loop_reset", "b2mpc_loop_post",
 ]
 
 
@@ -78,6 +80,9 @@ def lib():
         getattr(L, name).argtypes = [vp, i64, vp]
     L.b2mpc_solve_host.argtypes = [vp, i64] + [vp] * 11 + [vp]
     L.b2mpc_dfma_peak.argtypes = [C.c_int, dp]
+    L.b2mpc_obst_predict.argtypes = [vp, i64, i32, vp]
+    L.b2mpc_loop_reset.argtypes = [vp, i64, vp]
+    L.b2mpc_loop_post.argtypes = [vp, i64, vp, i32, i32, C.c_double, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("b2mpc_last_error", "b2mpc_default_config", "b2mpc_field_len", "b2mpc_workspace_bytes",

@@ -33,6 +33,7 @@ class BatchedMpcSolver:
             capi.ZZL: (N + 1, n_obst), capi.X: (N + 1, 5), capi.U: (N, 2), capi.SL: (N + 1, n_obst),
             capi.SU: (N + 1, n_obst), capi.PI: (N, 5), capi.LAM: (N + 1, 12 + 4 * n_obst),
             capi.T: (N + 1, 12 + 4 * n_obst), capi.STATS: (8,), capi.GOAL: (2,), capi.OBST: (n_obst, 4),
+            capi.MARGIN: (2,), capi.U0: (2,),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -85,7 +86,7 @@ class BatchedMpcSolver:
         return out
 
     def get_int(self, ifield, batch, host=False):
-        ifield = {"status": capi.STATUS, "qp_iter": capi.QP_ITER, "qp_status": capi.QP_STATUS}.get(ifield, ifield)
+        ifield = capi.IFIELD_NAMES.get(ifield, ifield)
         if host:
             out = np.empty(batch, np.int32)
             capi.check(capi.lib().b2mpc_get_i32_host(self._h, ifield, out.ctypes.data_as(C.c_void_p), batch, self._stream()))
@@ -118,6 +119,25 @@ class BatchedMpcSolver:
     def shift(self, batch):
         """warm-start shift, :253-258."""
         capi.check(capi.lib().b2mpc_shift(self._h, batch, self._stream()))
+
+    # -- closed loop around the solve (robot_ocp_problem.py:184-260) ------------------------------
+    def obst_predict(self, batch, quirk=True):
+        """parameterize_model(), :154-166: 'p' <- horizon prediction of 'obst' (visualization.py:62-79)."""
+        capi.check(capi.lib().b2mpc_obst_predict(self._h, batch, 1 if quirk else 0, self._stream()))
+
+    def loop_reset(self, batch):
+        capi.check(capi.lib().b2mpc_loop_reset(self._h, batch, self._stream()))
+
+    def loop_post(self, batch, noise=None, random_move=False, init_guess_when_error=True, tol=0.15):
+        """everything of one control step after solve(), :198-260; noise: CUDA tensor [B,M,2] ~ N(0,1)."""
+        npnt = None
+        if noise is not None:
+            noise = noise.to(self.torch.float64).contiguous()
+            assert noise.is_cuda and tuple(noise.shape) == (batch, self.M, 2)
+            npnt = C.c_void_p(noise.data_ptr())
+            self._keep_noise = noise
+        capi.check(capi.lib().b2mpc_loop_post(self._h, batch, npnt, 1 if random_move else 0,
+                                              1 if init_guess_when_error else 0, float(tol), self._stream()))
 
     def solve_host(self, x0, p, yref, zl, Zl, x, u, sl, su):
         """One control step on HOST numpy buffers (batch-first): copies in, solves, copies the iterate

@@ -130,3 +130,24 @@ def random_scenarios(B, dims: MpcDims = MpcDims(), seed=0, scenario="RANDOM", mo
     u = np.zeros((B, N, 2))
     sl = np.zeros((B, N + 1, M)); su = np.zeros((B, N + 1, M))
     return dict(x0=x0, goal=goal, obst=obst, p=p, yref=yref, zl=zl, Zl=Zl, x=x, u=u, sl=sl, su=su)
+
+
+def reference_episode_streams(seed, scenario="RANDOM", M=N_OBST, steps=400, random_move=True):
+    """The obstacle initial states and the velocity-noise stream ONE reference episode consumes after
+    `np.random.seed(seed)` (experiments.py:33-36): generate_random_moving_obstacles draws x, y (RANDOM
+    only), vx, vy as (M,1) uniforms (obstacle_generator.py:10-22); every control step then draws
+    `np.random.normal(size=2)` per obstacle in order (visualization.py:31).  Returns obst[M,4],
+    noise[steps,M,2] -- bit-identical to what the reference's global legacy RNG would produce."""
+    rs = np.random.RandomState(seed)
+    if scenario == "RANDOM":
+        xs = rs.uniform(X_MIN_OBST, X_MAX_OBST, (M, 1)); ys = rs.uniform(Y_MIN_OBST, Y_MAX_OBST, (M, 1))
+    elif scenario == "CENTER":
+        xs = np.zeros((M, 1)); ys = np.zeros((M, 1))
+    elif scenario == "EDGE":
+        xs = 7 * np.ones((M, 1)); ys = 7 * np.ones((M, 1))
+    else:
+        raise ValueError(scenario)
+    vx = rs.uniform(-V_MAX_OBST, V_MAX_OBST, (M, 1)); vy = rs.uniform(-V_MAX_OBST, V_MAX_OBST, (M, 1))
+    obst = np.hstack((xs, ys, vx, vy))
+    noise = rs.normal(size=(steps, M, 2)) if random_move else np.zeros((steps, M, 2))
+    return obst, noise

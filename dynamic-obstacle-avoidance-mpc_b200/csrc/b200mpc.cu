@@ -56,7 +56,7 @@ extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst,
 {
     memset(c, 0, sizeof(*c));
     c->N = N; c->n_obst = n_obst; c->device = device; c->max_batch = max_batch;
-    c->integrator = 0; c->qp_iter_max = 50; c->lm_scaled_by_dt = 0; c->kernel = 0;   // world_specification.py:48
+    c->integrator = 0; c->qp_iter_max = 50; c->lm_scaled_by_dt = 1; c->kernel = 0;   // world_specification.py:48
     c->pred_corr = 1; c->cond_pred_corr = 1; c->itref_corr_max = 2;
     c->tf = tf; c->lm = 2.0;                                       // robot_ocp_problem.py:128,132
     for (int i = 0; i < 4; i++) c->W[i] = 2.0;                     // Q = 2*I4, :26
@@ -130,6 +130,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     h->len[B2MPC_X] = (int64_t)(N + 1) * 5; h->len[B2MPC_U] = (int64_t)N * 2; h->len[B2MPC_PI] = (int64_t)N * 5;
     h->len[B2MPC_LAM] = h->len[B2MPC_T] = (int64_t)(N + 1) * h->nct;
     h->len[B2MPC_STATS] = 8; h->len[B2MPC_GOAL] = 2; h->len[B2MPC_OBST] = (int64_t)M * 4;
+    h->len[B2MPC_MARGIN] = 2; h->len[B2MPC_U0] = 2;
     int64_t maxlen = 0;
     for (int i = 0; i < B2MPC_N_FIELDS; i++) {
         if (h->len[i] > maxlen) maxlen = h->len[i];
@@ -414,6 +415,159 @@ extern "C" int b2mpc_shift(b2mpc* h, int64_t batch, void* stream)
     int rc = check_batch(h, batch);
     if (rc) return rc;
     b2_shift<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->f[B2MPC_X], h->f[B2MPC_U], h->N, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+
+// ------------------------------------------------------------------ closed loop around the solve
+// world_specification.py:7-10,28-31 (arena, obstacle radius/noise/speed limit)
+#define B2_XMIN (-8.0)
+#define B2_XMAX (8.0)
+#define B2_YMIN (-8.0)
+#define B2_YMAX (8.0)
+#define B2_R_OBST (1.0)
+#define B2_R_ROBOT (0.2)
+#define B2_RANDOMNESS (0.1)
+#define B2_V_MAX_OBST (2.0)
+
+// Obstacle.predict_step without noise, visualization.py:35-59
+__device__ __forceinline__ void b2_obst_move(double& x, double& vx, double& y, double& vy, double dt)
+{
+    double th;
+    if (vx < 0) th = (x - B2_XMIN) / fabs(vx);
+    else if (vx > 0) th = (B2_XMAX - x) / fabs(vx);
+    else th = INFINITY;
+    if (th <= dt) { x += (vx * th - vx * (dt - th)); vx = -vx; }
+    else x += vx * dt;
+    if (vy < 0) th = (y - B2_YMIN) / fabs(vy);
+    else if (vy > 0) th = (B2_YMAX - y) / fabs(vy);
+    else th = INFINITY;
+    if (th <= dt) { y += (vy * th - vy * (dt - th)); vy = -vy; }
+    else y += vy * dt;
+}
+
+// parameterize_model(): one thread per (problem, obstacle), robot_ocp_problem.py:154-166
+__global__ void b2_obst_predict(const double* __restrict__ OBST, double* __restrict__ P, const int32_t* __restrict__ DONE,
+                                int N, int M, double dt, int quirk, int B, int Bm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = t % B, j = t / B;
+    if (j >= M) return;
+    if (DONE[b]) return;
+    double x = OBST[((size_t)j * 4 + 0) * Bm + b], y = OBST[((size_t)j * 4 + 1) * Bm + b];
+    double vy = OBST[((size_t)j * 4 + 3) * Bm + b];
+    double vx = quirk ? vy : OBST[((size_t)j * 4 + 2) * Bm + b];        // `vx = self.vy`, visualization.py:69
+    P[((size_t)0 * 2 * M + 2 * j) * Bm + b] = x; P[((size_t)0 * 2 * M + 2 * j + 1) * Bm + b] = y;
+    for (int i = 0; i < N; i++) {
+        b2_obst_move(x, vx, y, vy, dt);
+        P[((size_t)(i + 1) * 2 * M + 2 * j) * Bm + b] = x; P[((size_t)(i + 1) * 2 * M + 2 * j + 1) * Bm + b] = y;
+    }
+}
+
+__global__ void b2_loop_reset(double* __restrict__ MARGIN, int32_t* STEPS, int32_t* DONE, int32_t* OOB, int32_t* NFAIL, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    MARGIN[b] = INFINITY; MARGIN[(size_t)Bm + b] = INFINITY;
+    STEPS[b] = 0; DONE[b] = 0; OOB[b] = 0; NFAIL[b] = 0;
+}
+
+// robot_ocp_problem.py:198-260 for one problem per thread
+__global__ void b2_loop_post(B2Params p, double* __restrict__ X0w, const double* __restrict__ GOAL, double* __restrict__ OBST,
+                             double* __restrict__ MARGIN, double* __restrict__ U0, int32_t* STEPS, int32_t* DONE, int32_t* OOB,
+                             int32_t* NFAIL, const double* __restrict__ noise, int random_move, int init_guess_when_error, double tol)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    if (DONE[b]) return;
+    const size_t Bm = (size_t)p.Bm;
+    const int N = p.N, M = p.M;
+    // u = ocp_solver.get(0,'u') (:198): on status 4 acados left the iterate untouched -> stale u0
+    double u[2] = {p.U[b], p.U[Bm + b]};
+    U0[b] = u[0]; U0[Bm + b] = u[1];
+    double x[5];
+    for (int i = 0; i < 5; i++) x[i] = X0w[i * Bm + b];
+    if (p.STATUS[b] == 4) {
+        NFAIL[b] += 1;
+        if (init_guess_when_error) {
+            // set_initial_guess(): reset + x_i <- x0 with v,omega zeroed IN x0 ITSELF (:301-302)
+            x[3] = 0.0; x[4] = 0.0;
+            for (int k = 0; k <= N; k++) {
+                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] = x[i];
+                if (k < N) { p.U[((size_t)k * 2) * Bm + b] = 0.0; p.U[((size_t)k * 2 + 1) * Bm + b] = 0.0; }
+                for (int j = 0; j < M; j++) { p.SL[((size_t)k * M + j) * Bm + b] = 0.0; p.SU[((size_t)k * M + j) * Bm + b] = 0.0; }
+            }
+        }
+    }
+    // plant step (:207-212)
+    double xn[5], sv[10];
+    if (p.integrator == 1) model_rk4_step(x, u, p.dt, xn, sv); else model_gl4_step(x, u, p.dt, xn, sv);
+    for (int i = 0; i < 5; i++) X0w[i * Bm + b] = xn[i];
+    if (xn[0] < B2_XMIN || xn[0] > B2_XMAX || xn[1] < B2_YMIN || xn[1] > B2_YMAX) OOB[b] = 1;   // :213-214
+    // obstacles move (:217-218) and margin bookkeeping (:222-228)
+    double min_margin = INFINITY;
+    for (int j = 0; j < M; j++) {
+        double ox = OBST[((size_t)j * 4 + 0) * Bm + b], oy = OBST[((size_t)j * 4 + 1) * Bm + b];
+        double vx = OBST[((size_t)j * 4 + 2) * Bm + b], vy = OBST[((size_t)j * 4 + 3) * Bm + b];
+        if (random_move && noise) {
+            const double n0 = noise[((size_t)b * M + j) * 2 + 0], n1 = noise[((size_t)b * M + j) * 2 + 1];
+            vx = fmin(fmax((1.0 + B2_RANDOMNESS * n0) * vx, -B2_V_MAX_OBST), B2_V_MAX_OBST);   // visualization.py:28-33
+            vy = fmin(fmax((1.0 + B2_RANDOMNESS * n1) * vy, -B2_V_MAX_OBST), B2_V_MAX_OBST);
+        }
+        b2_obst_move(ox, vx, oy, vy, p.dt);
+        OBST[((size_t)j * 4 + 0) * Bm + b] = ox; OBST[((size_t)j * 4 + 1) * Bm + b] = oy;
+        OBST[((size_t)j * 4 + 2) * Bm + b] = vx; OBST[((size_t)j * 4 + 3) * Bm + b] = vy;
+        const double margin = sqrt((xn[0] - ox) * (xn[0] - ox) + (xn[1] - oy) * (xn[1] - oy)) - (B2_R_OBST + B2_R_ROBOT);
+        if (margin < min_margin) min_margin = margin;
+    }
+    if (min_margin < MARGIN[b]) MARGIN[b] = min_margin;
+    // goal test on the position only (:246-250); the loop `break`s BEFORE i += 1 and before the shift
+    const double gx = GOAL[b], gy = GOAL[Bm + b];
+    const double dist = sqrt((xn[0] - gx) * (xn[0] - gx) + (xn[1] - gy) * (xn[1] - gy));
+    MARGIN[Bm + b] = dist;
+    if (dist <= tol) { DONE[b] = 1; return; }
+    // warm-start shift (:253-258)
+    for (int j = 0; j < N - 1; j++) {
+        for (int i = 0; i < 5; i++) p.X[((size_t)j * 5 + i) * Bm + b] = p.X[((size_t)(j + 1) * 5 + i) * Bm + b];
+        for (int i = 0; i < 2; i++) p.U[((size_t)j * 2 + i) * Bm + b] = p.U[((size_t)(j + 1) * 2 + i) * Bm + b];
+    }
+    for (int i = 0; i < 5; i++) p.X[((size_t)(N - 1) * 5 + i) * Bm + b] = p.X[((size_t)N * 5 + i) * Bm + b];
+    p.U[((size_t)(N - 1) * 2) * Bm + b] = 0.0; p.U[((size_t)(N - 1) * 2 + 1) * Bm + b] = 0.0;
+    STEPS[b] += 1;
+}
+
+extern "C" int b2mpc_obst_predict(b2mpc* h, int64_t batch, int32_t quirk, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    const int64_t n = batch * h->M;
+    b2_obst_predict<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->f[B2MPC_OBST], h->f[B2MPC_P], h->fi[B2MPC_DONE], h->N, h->M, h->prm.dt, quirk, (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_loop_reset(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    b2_loop_reset<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->f[B2MPC_MARGIN], h->fi[B2MPC_STEPS], h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], h->fi[B2MPC_NFAIL], (int)batch, h->Bm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_loop_post(b2mpc* h, int64_t batch, const double* dnoise, int32_t random_move,
+                               int32_t init_guess_when_error, double tol, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    B2Params p = h->prm;
+    p.B = (int)batch;
+    b2_loop_post<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        p, h->f[B2MPC_X0], h->f[B2MPC_GOAL], h->f[B2MPC_OBST], h->f[B2MPC_MARGIN], h->f[B2MPC_U0], h->fi[B2MPC_STEPS],
+        h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], h->fi[B2MPC_NFAIL], dnoise, random_move, init_guess_when_error, tol);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;

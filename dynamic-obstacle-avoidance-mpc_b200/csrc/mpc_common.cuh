@@ -122,3 +122,67 @@ __device__ __forceinline__ void b2_bat_p_ba(const double* sv, double h, double h
         for (int i = j; i < 7; i++) Mp[i * (i + 1) / 2 + j] = col[i];
     }
 }
+
+// ---- square-root helpers (thread-level) ---------------------------------------------------------
+// in-place Cholesky of a packed lower-triangular n x n matrix (idx(i,j) = i(i+1)/2 + j);
+// non-positive pivot -> zero column (BLASFEO dpotrf convention)
+template <int NN>
+__device__ __forceinline__ void b2_chol_packed(double* Mp)
+{
+#pragma unroll
+    for (int j = 0; j < NN; j++) {
+        double d = Mp[j * (j + 1) / 2 + j];
+#pragma unroll
+        for (int q = 0; q < j; q++) d -= Mp[j * (j + 1) / 2 + q] * Mp[j * (j + 1) / 2 + q];
+        const double l = d > 0.0 ? sqrt(d) : 0.0;
+        const double li = l > 0.0 ? 1.0 / l : 0.0;
+        Mp[j * (j + 1) / 2 + j] = l;
+#pragma unroll
+        for (int i = j + 1; i < NN; i++) {
+            double a = Mp[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int q = 0; q < j; q++) a -= Mp[i * (i + 1) / 2 + q] * Mp[j * (j + 1) / 2 + q];
+            Mp[i * (i + 1) / 2 + j] = a * li;
+        }
+    }
+}
+// y[5] = L (L^T x) for a packed lower 5x5 factor
+__device__ __forceinline__ void b2_llt_mul(const double* L, const double* x, double* y)
+{
+    double t[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = j; r < 5; r++) acc += L[b2_sym(r, j)] * x[r];
+        t[j] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; j++) acc += L[b2_sym(i, j)] * t[j];
+        y[i] = acc;
+    }
+}
+// Mp[28] (packed lower 7x7) = AL AL^T with AL = [B A]^T L  (L packed lower 5x5)
+__device__ __forceinline__ void b2_bat_l_sq(const double* sv, double h, double h2, const double* L, double* Mp)
+{
+    double AL[5][7];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        double col[5];
+#pragma unroll
+        for (int r = 0; r < 5; r++) col[r] = r >= q ? L[b2_sym(r, q)] : 0.0;
+        b2_bat_mul(sv, h, h2, col, AL[q]);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; q++) acc += AL[q][i] * AL[q][j];
+            Mp[i * (i + 1) / 2 + j] = acc;
+        }
+}

@@ -282,43 +282,37 @@ struct TppSolver {
                 const double cx = ws(k, o.cx + j), cy = ws(k, o.cy + j);
                 Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
             }
+            // square-root Riccati (HPIPM square_root_alg = 1): Pn holds Lxx, P = Lxx Lxx^T is never formed
+            // by subtraction (barrier weights reach 1e15+ near convergence; DESIGN.md "square-root Riccati")
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 15; i++) Pn[i] = 0.0;
 #pragma unroll
                 for (int i = 0; i < 5; i++) Pn[b2_sym(i, i)] = Hx[2 + i];
                 Pn[b2_sym(1, 0)] = hxy;
+                b2_chol_packed<5>(Pn);
             } else {
                 double sv[10], Mp[28];
                 load_sv(k, sv);
-                b2_bat_p_ba(sv, p.dt, p.dt2h, Pn, Mp);
+                b2_bat_l_sq(sv, p.dt, p.dt2h, Pn, Mp);
 #pragma unroll
                 for (int i = 0; i < 7; i++) Mp[i * (i + 1) / 2 + i] += Hx[i];
                 Mp[3 * 4 / 2 + 2] += hxy;
-                // 2x2 Cholesky of the control block
-                const double m00 = Mp[0], m10 = Mp[1], m11 = Mp[2];
-                const double l00 = m00 > 0.0 ? sqrt(m00) : 0.0;
-                const double l00i = l00 > 0.0 ? 1.0 / l00 : 0.0;
-                const double l10 = m10 * l00i;
-                const double d11 = m11 - l10 * l10;
-                const double l11 = d11 > 0.0 ? sqrt(d11) : 0.0;
-                const double l11i = l11 > 0.0 ? 1.0 / l11 : 0.0;
-                ws(k, o.lamu + 0) = l00i; ws(k, o.lamu + 1) = l10; ws(k, o.lamu + 2) = l11i;
+                b2_chol_packed<7>(Mp);
+                const double l00i = Mp[0] > 0.0 ? 1.0 / Mp[0] : 0.0, l11i = Mp[2] > 0.0 ? 1.0 / Mp[2] : 0.0;
+                ws(k, o.lamu + 0) = l00i; ws(k, o.lamu + 1) = Mp[1]; ws(k, o.lamu + 2) = l11i;
                 if (k > 0) {
-                    double L0[5], L1[5];
 #pragma unroll
                     for (int i = 0; i < 5; i++) {
                         const int r = 2 + i;
-                        L0[i] = Mp[r * (r + 1) / 2 + 0] * l00i;
-                        L1[i] = (Mp[r * (r + 1) / 2 + 1] - L0[i] * l10) * l11i;
-                        ws(k, o.lxu + 2 * i) = L0[i]; ws(k, o.lxu + 2 * i + 1) = L1[i];
+                        ws(k, o.lxu + 2 * i) = Mp[r * (r + 1) / 2 + 0]; ws(k, o.lxu + 2 * i + 1) = Mp[r * (r + 1) / 2 + 1];
                     }
 #pragma unroll
                     for (int i = 0; i < 5; i++)
 #pragma unroll
                         for (int j = 0; j <= i; j++) {
                             const int r = 2 + i, c = 2 + j;
-                            Pn[b2_sym(i, j)] = Mp[r * (r + 1) / 2 + c] - L0[i] * L0[j] - L1[i] * L1[j];
+                            Pn[b2_sym(i, j)] = Mp[r * (r + 1) / 2 + c];
                         }
                 }
             }
@@ -390,7 +384,7 @@ struct TppSolver {
                 for (int i = 0; i < 15; i++) Pn[i] = ws(k + 1, o.pm + i);
 #pragma unroll
                 for (int i = 0; i < 5; i++) rb[i] = ws(k, oRB + i);
-                b2_symv(Pn, rb, y);
+                b2_llt_mul(Pn, rb, y);
 #pragma unroll
                 for (int i = 0; i < 5; i++) y[i] += pn[i];
                 b2_bat_mul(sv, p.dt, p.dt2h, y, bt);
@@ -439,7 +433,7 @@ struct TppSolver {
                 for (int i = 0; i < 5; i++) xn[i] += ws(k, oRB + i);
 #pragma unroll
                 for (int i = 0; i < 15; i++) Pn[i] = ws(k + 1, o.pm + i);
-                b2_symv(Pn, xn, dpi);
+                b2_llt_mul(Pn, xn, dpi);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
                     dpi[i] += ws(k + 1, o.pv + i);

@@ -30,7 +30,7 @@ __constant__ unsigned char B2_BATAB[5][7] = {
 };
 
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, minv, kmat, pm, pv;                  // used by the sweeps
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv;                  // used by the sweeps
     int lam, t, tinv, dd;                                                       // per constraint (nct rows each); dd doubles as dlam
     int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrgsl, lrgsu, dsl, dsu, dli, dui, xu;
     int total;
@@ -39,7 +39,7 @@ struct WOff {
         const int nct = 12 + 4 * M;
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
-        cv = o; o += 7; cpi = o; o += 5; minv = o; o += 3; kmat = o; o += 10; pm = o; o += 15; pv = o; o += 5;
+        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5;
         lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
         b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
         zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
@@ -51,7 +51,8 @@ struct WOff {
 };
 
 __host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd row stride
-__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M) { return sizeof(double) * (size_t)WOff(M).total * b2_wpp_stride(N); }
+#define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
+__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M) { return sizeof(double) * ((size_t)WOff(M).total * b2_wpp_stride(N) + B2_WPP_SCRATCH); }
 
 __device__ __forceinline__ double b2_warp_max(double v)
 {
@@ -316,60 +317,78 @@ struct WppSolver {
         riccati_factorize();
     }
 
-    // backward Riccati recursion, sequential in the node index, lane e<28 owns entry (mi,mj) of
-    // M = Htilde + [B A]^T P+ [B A]; 2x2 control block factorised redundantly by all lanes
+    // Backward Riccati recursion in SQUARE-ROOT form (what HPIPM does with square_root_alg = 1):
+    //   AL = [B A]^T Lxx+ ,  M = Htilde + AL AL^T ,  L = chol(M) ,  pass Lxx on.
+    // The cost-to-go Hessian P = Lxx Lxx^T is never formed and never obtained by subtraction: near
+    // convergence the barrier weights on active state bounds reach 1e15+, where the classical recursion
+    // P = Mxx - Mxu Muu^-1 Mux loses all digits (and definiteness) -- see DESIGN.md "square-root Riccati".
+    // Lane e<28 owns entry (mi,mj) of the lower triangle; the 7 Cholesky columns are sequential.
     __device__ void riccati_factorize()
     {
         const int e = lane < 28 ? lane : 0;
         int mi = 0;
         while ((mi + 1) * (mi + 2) / 2 <= e) mi++;
         const int mj = e - mi * (mi + 1) / 2;
-        int ci[5], cj[5];
+        // phase A roles: lane owns AL entry (ai,aq) = lane, lanes 0..2 additionally entry 32+lane
+        const int ai0 = lane / 5, aq0 = lane % 5, ai1 = (32 + lane) / 5, aq1 = (32 + lane) % 5;
+        int ba0[5], ba1[5];
 #pragma unroll
-        for (int r = 0; r < 5; r++) { ci[r] = o.sv + B2_BATAB[r][mi]; cj[r] = o.sv + B2_BATAB[r][mj]; }
-        const int src_i0 = mi * (mi + 1) / 2, src_i1 = mi >= 1 ? src_i0 + 1 : 0;
-        const int src_j0 = mj * (mj + 1) / 2, src_j1 = mj >= 1 ? src_j0 + 1 : 0;
+        for (int r = 0; r < 5; r++) { ba0[r] = o.sv + B2_BATAB[r][ai0]; ba1[r] = o.sv + B2_BATAB[r][ai1 < 7 ? ai1 : 0]; }
         const bool xx = lane < 28 && mi >= 2 && mj >= 2;
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
-        const int prow = xx ? o.pm + b2_sym(mi - 2, mj - 2) : 0;
-        const int krow = xu ? o.kmat + 5 * mj + (mi - 2) : 0;
+        const int xrow = xx ? o.lxx + b2_sym(mi - 2, mj - 2) : 0;
+        const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
+        double* const scr = sm + o.total * NS;
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
             if (mi == mj) m = S(o.hg + mi, kk);
             if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
             if (kk < N) {
-                double P[15], w[5], a[5], c[5];
-#pragma unroll
-                for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, kk + 1);
-#pragma unroll
-                for (int r = 0; r < 5; r++) { a[r] = S(ci[r], kk); c[r] = S(cj[r], kk); }
-#pragma unroll
-                for (int r = 0; r < 5; r++) {
+                // A: AL = [B A]^T Lxx(kk+1)
+                {
                     double acc = 0.0;
 #pragma unroll
-                    for (int q = 0; q < 5; q++) acc += P[b2_sym(r, q)] * c[q];
-                    w[r] = acc;
+                    for (int r = 0; r < 5; r++) {
+                        const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
+                        acc += S(ba0[r], kk) * l;
+                    }
+                    scr[lane] = acc;
+                    if (lane < 3) {
+                        double acc1 = 0.0;
+#pragma unroll
+                        for (int r = 0; r < 5; r++) {
+                            const double l = (r >= aq1) ? S(o.lxx + b2_sym(r, aq1 <= r ? aq1 : r), kk + 1) : 0.0;
+                            acc1 += S(ba1[r], kk) * l;
+                        }
+                        scr[32 + lane] = acc1;
+                    }
                 }
+                __syncwarp();
+                // B: M = Htilde + AL AL^T
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < 5; r++) acc += a[r] * w[r];
+                for (int q = 0; q < 5; q++) acc += scr[mi * 5 + q] * scr[mj * 5 + q];
                 m += acc;
-                const double m00 = b2_bcast(m, 0), m10 = b2_bcast(m, 1), m11 = b2_bcast(m, 2);
-                // inverse of the 2x2 control block (positive definite: Hd + LM > 0)
-                const double det = m00 * m11 - m10 * m10;
-                const double di = (det > 0.0 && m00 > 0.0) ? 1.0 / det : 0.0;
-                const double i00 = m11 * di, i01 = -m10 * di, i11 = m00 * di;
-                const double mi0 = b2_bcast(m, src_i0), mi1 = b2_bcast(m, src_i1);
-                const double mj0 = b2_bcast(m, src_j0), mj1 = b2_bcast(m, src_j1);
-                // feedback gain K = -Muu^-1 Mux (column of node state mj-2 / mi-2)
-                const double Kj0 = -(i00 * mj0 + i01 * mj1), Kj1 = -(i01 * mj0 + i11 * mj1);
-                if (lane == 0) { S(o.minv + 0, kk) = i00; S(o.minv + 1, kk) = i01; S(o.minv + 2, kk) = i11; }
-                if (kk > 0) {
-                    if (xx) S(prow, kk) = m + mi0 * Kj0 + mi1 * Kj1;           // P = Mxx + Mxu K
-                    if (xu) S(krow, kk) = (mj == 0) ? -(i00 * mi0 + i01 * mi1) : -(i01 * mi0 + i11 * mi1);
-                }
-            } else {
-                if (xx) S(prow, kk) = m;
+            }
+            // C: right-looking Cholesky, one column at a time (non-positive pivot -> zero column, as BLASFEO)
+            double rs0 = 0.0, rs1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 7; c++) {
+                const double d = b2_bcast(m, c * (c + 1) / 2 + c);
+                const double rs = d > 0.0 ? rsqrt(d) : 0.0;
+                if (c == 0) rs0 = rs;
+                if (c == 1) rs1 = rs;
+                const double lc = m * rs;                                   // valid on lanes with mj == c
+                const double la = b2_bcast(lc, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
+                const double lb = b2_bcast(lc, mj * (mj + 1) / 2 + (c <= mj ? c : mj));
+                if (mj > c) m -= la * lb;
+                else if (mj == c) m = lc;
+            }
+            if (kk < N && lane == 0) { S(o.lamu + 0, kk) = rs0; S(o.lamu + 2, kk) = rs1; }
+            if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;                 // l10
+            if (kk > 0) {
+                if (xx) S(xrow, kk) = m;
+                if (xu) S(lrow, kk) = m;
             }
             __syncwarp();
         }
@@ -453,28 +472,46 @@ struct WppSolver {
         __syncwarp();
     }
 
+    // y = Lxx(kk) (Lxx(kk)^T x): product with the cost-to-go Hessian through its factor
+    __device__ __forceinline__ void ctg_mul(int kk, const double* x, double* y) const
+    {
+        double L[15], t[5];
+#pragma unroll
+        for (int i = 0; i < 15; i++) L[i] = S(o.lxx + i, kk);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = j; r < 5; r++) acc += L[b2_sym(r, j)] * x[r];
+            t[j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j <= i; j++) acc += L[b2_sym(i, j)] * t[j];
+            y[i] = acc;
+        }
+    }
+
     // backward + forward vector sweeps with the current factorisation.  Everything that does not
-    // depend on the recursion (z_k = P+ rb_k before, dpi_k = P+ dx+ + p+ after) is node-parallel; the
-    // sequential cores are  p_k = gx + A^T s + K^T w,  w = gu + B^T s,  s = p+ + z   (lanes 0..4 own the
-    // components, w is computed redundantly) and  dx+ = A dx + B du + rb,  du = K dx + kff.
+    // depend on the recursion (z_k = P+ rb_k before, dpi_k = P+ dx+ + p+ after, both through the factor)
+    // is node-parallel; the sequential cores are
+    //   backward:  s = p+ + z,  w = gu + B^T s,  lu = Luu^-1 w,  p = gx + A^T s - Lxu lu
+    //   forward :  du = -Luu^-T (lu + Lxu^T dx),  dx+ = A dx + B du + rb
+    // (lanes 0..4 own the components, 2-vectors are computed redundantly by every lane).
     // kind 3 reads the linear residual (lrb) and writes the correction to cv/cpi.
     __device__ void riccati_solve(int kind)
     {
         const bool itr = (kind == 3);
         const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.dv, oDPI = itr ? o.cpi : o.dpi;
         if (act && k < N) {
-            double P[15], rb[5];
-#pragma unroll
-            for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, k + 1);
+            double rb[5], z[5];
 #pragma unroll
             for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
+            ctg_mul(k + 1, rb, z);
 #pragma unroll
-            for (int i = 0; i < 5; i++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 5; q++) acc += P[b2_sym(i, q)] * rb[q];
-                S(oDPI + i, k) = acc;                                   // z_k (overwritten by dpi_k below)
-            }
+            for (int i = 0; i < 5; i++) S(oDPI + i, k) = z[i];            // z_k (overwritten by dpi_k below)
         }
         __syncwarp();
         const int c5 = lane < 5 ? lane : 4;
@@ -499,13 +536,14 @@ struct WppSolver {
             // short dependency trees: the chain through this loop is the critical path of a solve
             const double w0 = (S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0]) + (S(o.sv + SV_B10, kk) * s[1] + h * s[3]);
             const double w1 = (S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0]) + (S(o.sv + SV_B11, kk) * s[1] + h2 * s[2]) + h * s[4];
-            const double i00 = S(o.minv + 0, kk), i01 = S(o.minv + 1, kk), i11 = S(o.minv + 2, kk);
-            const double kff0 = -(i00 * w0 + i01 * w1), kff1 = -(i01 * w0 + i11 * w1);
-            if (lane == 0) { S(oDV + 0, kk) = kff0; S(oDV + 1, kk) = kff1; }
+            const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+            const double lu0 = w0 * l00i;
+            const double lu1 = (w1 - l10 * lu0) * l11i;
+            if (lane == 0) { S(oDV + 0, kk) = lu0; S(oDV + 1, kk) = lu1; }
             if (kk > 0) {
                 const double pa = (S(o.hg + 2 + c5, kk) + S(acol[0], kk) * s[0]) + (S(acol[1], kk) * s[1] + S(acol[2], kk) * s[2]);
                 const double pb = S(acol[3], kk) * s[3] + S(acol[4], kk) * s[4];
-                const double pc = (pa + pb) + (S(o.kmat + c5, kk) * w0 + S(o.kmat + 5 + c5, kk) * w1);
+                const double pc = (pa + pb) - (S(o.lxu + 2 * c5, kk) * lu0 + S(o.lxu + 2 * c5 + 1, kk) * lu1);
                 if (lane < 5) S(o.pv + lane, kk) = pc;
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
@@ -516,11 +554,14 @@ struct WppSolver {
         double dx[5] = {0, 0, 0, 0, 0};
         if (lane < 5) S(oDV + 2 + lane, 0) = 0.0;
         for (int kk = 0; kk < N; kk++) {
-            double du0 = S(oDV + 0, kk), du1 = S(oDV + 1, kk);
+            double r0 = S(oDV + 0, kk), r1 = S(oDV + 1, kk);
             if (kk > 0) {
-                du0 = (du0 + S(o.kmat + 0, kk) * dx[0] + S(o.kmat + 1, kk) * dx[1]) + (S(o.kmat + 2, kk) * dx[2] + S(o.kmat + 3, kk) * dx[3] + S(o.kmat + 4, kk) * dx[4]);
-                du1 = (du1 + S(o.kmat + 5, kk) * dx[0] + S(o.kmat + 6, kk) * dx[1]) + (S(o.kmat + 7, kk) * dx[2] + S(o.kmat + 8, kk) * dx[3] + S(o.kmat + 9, kk) * dx[4]);
+                r0 = (r0 + S(o.lxu + 0, kk) * dx[0] + S(o.lxu + 2, kk) * dx[1]) + (S(o.lxu + 4, kk) * dx[2] + S(o.lxu + 6, kk) * dx[3] + S(o.lxu + 8, kk) * dx[4]);
+                r1 = (r1 + S(o.lxu + 1, kk) * dx[0] + S(o.lxu + 3, kk) * dx[1]) + (S(o.lxu + 5, kk) * dx[2] + S(o.lxu + 7, kk) * dx[3] + S(o.lxu + 9, kk) * dx[4]);
             }
+            const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+            const double du1 = -r1 * l11i;
+            const double du0 = (-r0 - l10 * du1) * l00i;
             const double xa = (S(oRB + c5, kk) + S(arow[2], kk) * dx[0] + S(arow[3], kk) * dx[1]) + (S(arow[4], kk) * dx[2] + S(arow[5], kk) * dx[3] + S(arow[6], kk) * dx[4]);
             const double xn = xa + (S(arow[0], kk) * du0 + S(arow[1], kk) * du1);
             if (lane == 0) { S(oDV + 0, kk) = du0; S(oDV + 1, kk) = du1; }
@@ -531,18 +572,12 @@ struct WppSolver {
         if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
         __syncwarp();
         if (act && k < N) {
-            double P[15], dxn[5];
-#pragma unroll
-            for (int i = 0; i < 15; i++) P[i] = S(o.pm + i, k + 1);
+            double dxn[5], y[5];
 #pragma unroll
             for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
+            ctg_mul(k + 1, dxn, y);
 #pragma unroll
-            for (int i = 0; i < 5; i++) {
-                double acc = S(o.pv + i, k + 1);
-#pragma unroll
-                for (int q = 0; q < 5; q++) acc += P[b2_sym(i, q)] * dxn[q];
-                S(oDPI + i, k) = acc;
-            }
+            for (int i = 0; i < 5; i++) S(oDPI + i, k) = y[i] + S(o.pv + i, k + 1);
         }
         __syncwarp();
     }

@@ -77,9 +77,16 @@ enum {
     B2MPC_STATS = 12, /* [8] res_g,res_b,res_d,res_m,mu,alpha,n_itref,0 at exit (output)     */
     B2MPC_GOAL = 13,  /* [2]            sub-goal used by b2mpc_prepare_slack / closed loop   */
     B2MPC_OBST = 14,  /* [M*4]          obstacle states (x,y,vx,vy), visualization.py:10-18  */
-    B2MPC_N_FIELDS = 15
+    B2MPC_MARGIN = 15, /* [2]           closed loop: min_margin_traj, distance_to_goal (:222-228,:246) */
+    B2MPC_U0 = 16,    /* [2]            control applied by the last b2mpc_loop_post (get(0,'u'), :198) */
+    B2MPC_N_FIELDS = 17
 };
-enum { B2MPC_STATUS = 0, B2MPC_QP_ITER = 1, B2MPC_QP_STATUS = 2, B2MPC_N_IFIELDS = 3 };
+enum { B2MPC_STATUS = 0, B2MPC_QP_ITER = 1, B2MPC_QP_STATUS = 2,
+       B2MPC_STEPS = 3,   /* closed loop: control steps taken (i of :184-260) */
+       B2MPC_DONE = 4,    /* closed loop: reached the goal tolerance (reached_subgoal, :247-250) */
+       B2MPC_OOB = 5,     /* closed loop: left the arena at least once (:213-214) */
+       B2MPC_NFAIL = 6,   /* closed loop: number of status-4 solves (:203) */
+       B2MPC_N_IFIELDS = 7 };
 enum { B2MPC_LAYOUT_SOA = 0, B2MPC_LAYOUT_AOS = 1 };
 
 enum {
@@ -123,6 +130,20 @@ int b2mpc_solve(b2mpc *h, int64_t batch, void *stream);
 int b2mpc_sim(b2mpc *h, int64_t batch, void *stream);
 /* warm-start shift, :253-258 */
 int b2mpc_shift(b2mpc *h, int64_t batch, void *stream);
+/* ---- closed loop around the solve: everything of robot_ocp_problem.py:184-260
+ * that is not the solve itself, on device ---- */
+/* parameterize_model(), :154-166 + Obstacle.predict_trajectory, visualization.py:62-79:
+ * P <- predicted obstacle positions over the horizon from OBST; quirk_vx_is_vy reproduces :69 */
+int b2mpc_obst_predict(b2mpc *h, int64_t batch, int32_t quirk_vx_is_vy, void *stream);
+/* zero the closed-loop bookkeeping (init_experiment, :35-52) */
+int b2mpc_loop_reset(b2mpc *h, int64_t batch, void *stream);
+/* the rest of one control step after b2mpc_solve, :198-260: read u0, on status 4 re-initialise the
+ * guess (init_guess_when_error, incl. the x0 aliasing quirk), plant step, out-of-bounds flag, obstacle
+ * step with noise[batch][M][2] ~ N(0,1) (device, batch-first; NULL or random_move=0: no noise),
+ * margins, goal test with tolerance `tol`, warm-start shift.  Finished problems are frozen. */
+int b2mpc_loop_post(b2mpc *h, int64_t batch, const double *dnoise, int32_t random_move,
+                    int32_t init_guess_when_error, double tol, void *stream);
+
 /* which solve kernel the handle resolved to: 1 = thread-per-problem (generic), 2 = warp-per-problem */
 int b2mpc_kernel(const b2mpc *h);
 /* number of kernels launched by this handle so far (for bench accounting) */

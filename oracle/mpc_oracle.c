@@ -34,7 +34,7 @@ void orc_default_config(orc_config *c, int N, int M, double tf)
     memset(c, 0, sizeof(*c));
     c->N = N; c->M = M; c->integrator = 0; c->soft = 1;
     c->qp_iter_max = 50;                      /* world_specification.py:48 */
-    c->lm_scaled_by_dt = 0;
+    c->lm_scaled_by_dt = 1;   /* see DESIGN.md "Levenberg-Marquardt scaling": fixtures favour Ts*lm */
     c->pred_corr = 1; c->cond_pred_corr = 1; c->itref_corr_max = 2;
     c->tf = tf; c->lm = 2.0;                  /* robot_ocp_problem.py:128,132 */
     /* W = blkdiag(Q=2*I4, R=0.15*I2), robot_ocp_problem.py:24-26,78-80 */
@@ -512,6 +512,34 @@ static void ipm_fact(const orc_config *c, ipm_mem *m)
         }
         for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) w->L[i][j] = Mx[i][j];
         chol_ln(w->L, nv);
+        if (c->reserved == 1 && nu == 2 && q->nx == NX) {
+            /* DEBUG/ANALYSIS ONLY: classical Riccati -- replace Lxx by chol(Mxx - Mxu Muu^-1 Mux) with the
+             * Schur complement formed explicitly through the 2x2 inverse (what a naive GPU kernel would do) */
+            double det = Mx[0][0] * Mx[1][1] - Mx[1][0] * Mx[1][0], di = 1.0 / det;
+            double i00 = Mx[1][1] * di, i01 = -Mx[1][0] * di, i11 = Mx[0][0] * di;
+            double P[NX][NX];
+            for (int i = 0; i < NX; i++) for (int j = 0; j < NX; j++) {
+                double k0 = -(i00 * Mx[2 + j][0] + i01 * Mx[2 + j][1]), k1 = -(i01 * Mx[2 + j][0] + i11 * Mx[2 + j][1]);
+                P[i][j] = Mx[2 + i][2 + j] + Mx[2 + i][0] * k0 + Mx[2 + i][1] * k1;
+            }
+#ifdef ORC_DEBUG
+            {   double maxrel = 0, maxabs = 0, pmax = 0, pmin = 1e300;
+                for (int i = 0; i < NX; i++) for (int j = 0; j <= i; j++) {
+                    double ps = 0; for (int r = 0; r <= j; r++) ps += w->L[2 + i][2 + r] * w->L[2 + j][2 + r];
+                    double d = fabs(ps - P[i][j]); if (d > maxabs) maxabs = d;
+                    if (fabs(ps) > pmax) pmax = fabs(ps);
+                    if (i == j && fabs(ps) < pmin) pmin = fabs(ps);
+                }
+                double mmax = 0; for (int i = 0; i < nv; i++) if (fabs(Mx[i][i]) > mmax) mmax = fabs(Mx[i][i]);
+                if (maxabs > 1e-7 * pmin) fprintf(stderr, "  stage %d: |P_cl-P_sqrt| %.2e  max|P| %.2e min diag P %.2e  max diag M %.2e det %.3e m00 %.3e m11 %.3e\n", k, maxabs, pmax, pmin, mmax, det, Mx[0][0], Mx[1][1]);
+            }
+#endif
+            double Lx[NV][NV];
+            memset(Lx, 0, sizeof(Lx));
+            for (int i = 0; i < NX; i++) for (int j = 0; j < NX; j++) Lx[i][j] = P[i][j];
+            chol_ln(Lx, NX);
+            for (int i = 0; i < NX; i++) for (int j = 0; j < NX; j++) w->L[2 + i][2 + j] = Lx[i][j];
+        }
         (void)nu;
     }
 }

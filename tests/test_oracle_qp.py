@@ -88,7 +88,7 @@ def test_ipm_solution_satisfies_kkt(oracle, N, M, tf):
 
 def test_qp_data_matches_survey_appendix_a(oracle):
     """Hessian/gradient diagonals of SURVEY Appendix A: H_k = dt*diag(.15,.15,2,2,0,2,2)+2I."""
-    cfg = oracle.default_config(20, 5, 2.0)
+    cfg = oracle.default_config(20, 5, 2.0, lm_scaled_by_dt=0)      # SURVEY App. A quotes the unscaled variant
     sc = world.random_scenarios(1, world.MpcDims(), seed=0)
     a = [sc[k][0] for k in ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")]
     q = oracle.export_qp(cfg, *a)
@@ -103,7 +103,8 @@ def test_qp_data_matches_survey_appendix_a(oracle):
     zl = sc["zl"][0]
     assert np.allclose(q["Zl"][3], 0.1 * zl[3]) and np.allclose(q["zl"][3], 0.1 * zl[3])
     assert np.allclose(q["Zl"][20], 0.0)
-    cfg2 = oracle.default_config(20, 5, 2.0, lm_scaled_by_dt=1)
+    cfg2 = oracle.default_config(20, 5, 2.0)                         # default: Ts * levenberg_marquardt
+    assert cfg2.lm_scaled_by_dt == 1
     q2 = oracle.export_qp(cfg2, *a)
     assert np.allclose(np.diag(q2["H"][3]), [0.215, 0.215, 0.4, 0.4, 0.2, 0.4, 0.4])
 
