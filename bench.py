@@ -160,7 +160,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from b200mpc import BatchedMpcSolver, dfma_peak_tflops, flops, world
+    from b200mpc import BatchedMpcSolver, dfma_peak_tflops, flops, sharding, world
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,8 +175,9 @@ def main():
 
     B = a.batch_per_gpu
     dims = world.MpcDims(a.N, a.n_obst, a.tf)
-    # env-sharded: rank r owns scenarios [r*B, (r+1)*B) of the global seeded set (no cross-GPU traffic)
-    sc = world.random_scenarios(B, dims, seed=a.seed + 1000 * rank)
+    # env-sharded: rank r owns the contiguous chunk [r*B, (r+1)*B) of ONE global seeded scenario set;
+    # no cross-GPU traffic until the final reduction of a few scalars
+    sc = sharding.shard_dict(world.random_scenarios(B * world_size, dims, seed=a.seed), rank, world_size)
     solver = BatchedMpcSolver(a.N, a.n_obst, a.tf, max_batch=B, device=local_rank, kernel=a.kernel)
     names_in = ("x0", "p", "yref", "zl", "Zl")
     names_it = ("x", "u", "sl", "su")
@@ -250,13 +251,10 @@ def main():
     assert np.array_equal(host_it["u"], solver.get("u", B).cpu().numpy())
 
     # ---------------- reduce over ranks (max time; sum of work) ----------------
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    s = torch.tensor([float(B), float(qp_iter.sum()), float((status != 0).sum())], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_s_max = t.tolist()
-    tot_B, tot_it, tot_fail = s.tolist()
+    sums, maxs = sharding.reduce_stats({"B": B, "qp_iter": float(qp_iter.sum()), "fail": float((status != 0).sum())},
+                                       {"total_ms": total_ms, "e2e_s": e2e_s}, device=dev)
+    total_ms_max, e2e_s_max = maxs["total_ms"], maxs["e2e_s"]
+    tot_B, tot_it, tot_fail = sums["B"], sums["qp_iter"], sums["fail"]
 
     if rank == 0:
         ms_per_step = total_ms_max / a.steps
