@@ -370,20 +370,37 @@ struct WppSolver {
                 for (int q = 0; q < 5; q++) acc += scr[mi * 5 + q] * scr[mj * 5 + q];
                 m += acc;
             }
-            // C: right-looking Cholesky, one column at a time (non-positive pivot -> zero column, as BLASFEO)
-            double rs0 = 0.0, rs1 = 0.0;
+            // C: right-looking Cholesky with DELAYED NORMALISATION.  The sequential chain per column is one
+            // shuffle round + two FMAs: instead of T_ik -= T_ic T_kc / T_cc (rsqrt/division on the critical
+            // path) the scaled Schur complement S = sigma * T is updated fraction-free,
+            //     S_ik <- (S_ik p - S_ic S_kc) * 2^-e(p),   sigma <- sigma * p 2^-e(p),   p = S_cc,
+            // (the power of two keeps sigma in [1, 2^7)), and each lane normalises its own column once at
+            // the end: L_ic = S_ic / sqrt(sigma_c p_c).  Non-positive pivot -> zero column, as BLASFEO.
+            double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
 #pragma unroll
             for (int c = 0; c < 7; c++) {
-                const double d = b2_bcast(m, c * (c + 1) / 2 + c);
-                const double rs = d > 0.0 ? rsqrt(d) : 0.0;
-                if (c == 0) rs0 = rs;
-                if (c == 1) rs1 = rs;
-                const double lc = m * rs;                                   // valid on lanes with mj == c
-                const double la = b2_bcast(lc, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
-                const double lb = b2_bcast(lc, mj * (mj + 1) / 2 + (c <= mj ? c : mj));
-                if (mj > c) m -= la * lb;
-                else if (mj == c) m = lc;
+                const double pv_ = b2_bcast(m, c * (c + 1) / 2 + c);
+                const double la = b2_bcast(m, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
+                const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (c <= mj ? c : mj));
+                const bool ok = pv_ > 0.0;
+                const double sp = ok ? sigma * pv_ : 0.0;
+                if (c == 0) sp0 = sp;
+                if (mj == c) my_sp = sp;
+                if (ok) {
+                    const int ex = ((__double2hiint(pv_) >> 20) & 0x7ff) - 1023;
+                    const double scale = __hiloint2double((1023 - ex) << 20, 0);
+                    const double pn = pv_ * scale;
+                    if (mj > c) m = m * pn - (la * lb) * scale;
+                    sigma *= pn;
+                }
             }
+            // one rsqrt per lane (its own column); 1/L00 and 1/L11 come from the diagonal lanes 0 and 2:
+            //   1/L00 = rsqrt(p_0),  1/L11 = sqrt(sigma_1/p_1) = sigma_1 rsqrt(sigma_1 p_1),  sigma_1 = p_0 2^-e(p_0)
+            const double myrs = my_sp > 0.0 ? rsqrt(my_sp) : 0.0;
+            m *= myrs;
+            const double rs0 = b2_bcast(myrs, 0);
+            const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double((1023 - (((__double2hiint(sp0) >> 20) & 0x7ff) - 1023)) << 20, 0) : 1.0;
+            const double rs1 = sig1 * b2_bcast(myrs, 2);
             if (kk < N && lane == 0) { S(o.lamu + 0, kk) = rs0; S(o.lamu + 2, kk) = rs1; }
             if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;                 // l10
             if (kk > 0) {
