@@ -72,9 +72,14 @@ class BatchedRobotOcp:
     def step(self, max_iter, check_every=8):
         """Run the RTI closed loop for at most max_iter control steps per environment.
         Returns (x_final[B,5], hit[B], reached[B], min_margin[B], dist_to_goal[B], steps[B], out_of_bounds[B])."""
-        s, B, torch = self.solver, self.B, self.torch
         self.set_initial_guess()
-        for i in range(max_iter):
+        self.advance(max_iter, check_every)
+        return self.outcome()
+
+    def advance(self, n_steps, check_every=8):
+        """the `while i < max_iter` loop body (:184-260) n_steps times, without re-initialising the guess"""
+        s, B, torch = self.solver, self.B, self.torch
+        for i in range(n_steps):
             s.obst_predict(B, quirk=self.quirk_prediction)          # parameterize_model(), :186
             s.prepare_slack(B)                                       # parameterize_slack(), :188
             s.solve(B)                                               # :191-195 (x0 embedding is the 'x0' field)
@@ -86,6 +91,9 @@ class BatchedRobotOcp:
             self._step_count += 1
             if (i + 1) % check_every == 0 and bool(s.get_int("done", B).all()):
                 break
+
+    def outcome(self):
+        s, B = self.solver, self.B
         margin = s.get("margin", B, host=True)
         x0 = s.get("x0", B, host=True)
         return (x0, margin[:, 0] <= 0, s.get_int("done", B, host=True).astype(bool), margin[:, 0], margin[:, 1],

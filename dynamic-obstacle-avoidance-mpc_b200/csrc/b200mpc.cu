@@ -142,9 +142,6 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         if (cudaMalloc(&h->fi[i], sizeof(int32_t) * h->Bm) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(int field) failed"); }
         cudaMemset(h->fi[i], 0, sizeof(int32_t) * h->Bm);
     }
-    h->ws_bytes = sizeof(double) * (size_t)B2Off(M).total * (N + 1) * h->Bm;
-    if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(workspace, %zu B) failed", h->ws_bytes); }
-    cudaMemset(h->ws, 0, h->ws_bytes);
     h->stage_elems = (size_t)maxlen * h->Bm;
     if (cudaMalloc(&h->stage_d, sizeof(double) * h->stage_elems) != cudaSuccess ||
         cudaMallocHost(&h->stage_h, sizeof(double) * h->stage_elems) != cudaSuccess ||
@@ -164,6 +161,13 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         return fail(B2MPC_EINVAL, "warp-per-problem kernel needs N+1 <= 32 and %zu B <= %d B of shared memory", b2_wpp_smem_bytes(N, M), max_smem);
     }
     h->kernel = (cfg->kernel == 1) ? 1 : (cfg->kernel == 2 ? 2 : (wpp_ok ? 2 : 1));
+    // global scratch is only needed by the thread-per-problem kernel (the warp kernel lives on chip)
+    h->ws_bytes = h->kernel == 1 ? sizeof(double) * (size_t)B2Off(M).total * (N + 1) * h->Bm : 0;
+    if (h->ws_bytes) {
+        if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(workspace, %zu B) failed", h->ws_bytes); }
+        cudaMemset(h->ws, 0, h->ws_bytes);
+    }
+    h->prm.WS = h->ws;
     if (h->kernel == 2) {
         cudaError_t e = (M == 5 && N == 20) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
                       : (M == 5)            ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)

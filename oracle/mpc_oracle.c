@@ -245,11 +245,20 @@ static ipm_mem *ipm_alloc(int N)
     m->rm_bkp = (double *)calloc((size_t)(N + 1) * MAXC, sizeof(double));
     return m;
 }
-static void ipm_free(ipm_mem *m)
+static void ipm_free_real(ipm_mem *m)
 {
     free(m->qp); free(m->sol); free(m->step); free(m->corr); free(m->res); free(m->lin);
     free(m->ws); free(m->rm_bkp); free(m);
 }
+/* one cached workspace per thread (a solver object reuses its memory between solves, as acados does) */
+static _Thread_local ipm_mem *tl_mem = NULL;
+static ipm_mem *ipm_get(int N)
+{
+    if (tl_mem && tl_mem->N != N) { ipm_free_real(tl_mem); tl_mem = NULL; }
+    if (!tl_mem) tl_mem = ipm_alloc(N);
+    return tl_mem;
+}
+static void ipm_free(ipm_mem *m) { (void)m; }
 
 /* ------------------------------------------------ RTI preparation: build QP */
 /* SURVEY App. A/B.  Node 0 is emitted with x0 already eliminated (HPIPM
@@ -891,7 +900,7 @@ int orc_rti_solve(const orc_config *c, const double *x0bar, const double *p,
                   int32_t *qp_iter, int32_t *qp_status, double *stats)
 {
     const int N = c->N, M = c->M;
-    ipm_mem *m = ipm_alloc(N);
+    ipm_mem *m = ipm_get(N);
     double dx0[NX];
     build_qp(c, x0bar, p, yref, zl, Zl, x, u, sl, su, m->qp, dx0);
     int it = 0;
@@ -1044,7 +1053,7 @@ int orc_qp_solve_export(const orc_config *c, const double *x0bar, const double *
                   int32_t *qp_iter, int32_t *qp_status, double *stats)
 {
     const int N = c->N, M = c->M;
-    ipm_mem *m = ipm_alloc(N);
+    ipm_mem *m = ipm_get(N);
     double dx0[NX];
     build_qp(c, x0bar, p, yref, zl, Zl, x, u, sl, su, m->qp, dx0);
     int it = 0;
