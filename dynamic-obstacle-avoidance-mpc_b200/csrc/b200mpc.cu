@@ -44,6 +44,7 @@ struct b2mpc {
     int32_t* stage_hi;
     size_t stage_elems;
     int64_t launches;
+    int32_t* order;                  // launch order for the warp kernel + 2 counters
     int kernel;                      // resolved: 1 thread-per-problem, 2 warp-per-problem
     size_t wpp_smem;
     B2Params prm;
@@ -169,6 +170,9 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     }
     h->prm.WS = h->ws;
     if (h->kernel == 2) {
+        if (cudaMalloc(&h->order, sizeof(int32_t) * ((size_t)h->Bm + 2)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
+    }
+    if (h->kernel == 2) {
         cudaError_t e = (M == 5 && N == 20) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
                       : (M == 5)            ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
                                             : cudaFuncSetAttribute(b2_rti_solve_wpp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
@@ -186,6 +190,7 @@ extern "C" int b2mpc_destroy(b2mpc* h)
     for (int i = 0; i < B2MPC_N_FIELDS; i++) if (h->f[i]) cudaFree(h->f[i]);
     for (int i = 0; i < B2MPC_N_IFIELDS; i++) if (h->fi[i]) cudaFree(h->fi[i]);
     if (h->ws) cudaFree(h->ws);
+    if (h->order) cudaFree(h->order);
     if (h->stage_d) cudaFree(h->stage_d);
     if (h->stage_h) cudaFreeHost(h->stage_h);
     if (h->stage_hi) cudaFreeHost(h->stage_hi);
@@ -577,6 +582,27 @@ extern "C" int b2mpc_loop_post(b2mpc* h, int64_t batch, const double* dnoise, in
     return B2MPC_OK;
 }
 
+// Launch-order heuristic for the warp kernel.  Interior-point iteration counts range from 13 to the limit;
+// problems whose linearisation point lies inside an obstacle's safety disc (negative h somewhere on the
+// horizon) are the slow ones (mu0 = 1 against multipliers ~1e5).  CTAs are dispatched in index order, so
+// putting those first shortens the tail of the launch.  Pure scheduling: per-problem results are unaffected.
+__global__ void b2_order_problems(const double* __restrict__ X, const double* __restrict__ P, int32_t* __restrict__ order,
+                                  int32_t* __restrict__ cnt, int N, int M, double r2, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    bool inside = false;
+    for (int k = 0; k <= N && !inside; k += 4) {
+        const double x = X[((size_t)k * 5 + 0) * Bm + b], y = X[((size_t)k * 5 + 1) * Bm + b];
+        for (int j = 0; j < M; j++) {
+            const double dx = x - P[((size_t)k * 2 * M + 2 * j) * Bm + b], dy = y - P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b];
+            inside |= (dx * dx + dy * dy < r2);
+        }
+    }
+    if (inside) order[atomicAdd(&cnt[0], 1)] = b;
+    else order[B - 1 - atomicAdd(&cnt[1], 1)] = b;
+}
+
 // ------------------------------------------------------------------ the solve
 extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
 {
@@ -586,6 +612,12 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     B2Params p = h->prm;
     p.B = (int)batch;
     if (h->kernel == 2) {
+        int32_t* cnt = h->order + h->Bm;
+        CUDA_TRY(cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), st));
+        b2_order_problems<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], h->order, cnt, h->N, h->M,
+                                                                         h->cfg.r2, (int)batch, h->Bm);
+        h->launches++;
+        p.ORDER = h->order;
         const unsigned blocks = (unsigned)batch;          // one warp-CTA per problem
         if (h->M == 5 && h->N == 20) b2_rti_solve_wpp<5, 20><<<blocks, 32, h->wpp_smem, st>>>(p);
         else if (h->M == 5) b2_rti_solve_wpp<5, 0><<<blocks, 32, h->wpp_smem, st>>>(p);

@@ -60,6 +60,7 @@ struct B2Params {
     // outputs
     double *PI, *LAM, *T, *STATS;
     int32_t *STATUS, *QP_ITER, *QP_STATUS;
+    const int32_t* ORDER;        // optional launch order of the problems (warp kernel)
     // scratch
     double* WS;
 };

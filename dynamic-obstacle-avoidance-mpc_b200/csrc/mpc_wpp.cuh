@@ -907,7 +907,8 @@ template <int MT, int NT>
 __global__ void __launch_bounds__(32) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    for (int i = blockIdx.x; i < p.B; i += gridDim.x) {
+        const int b = p.ORDER ? p.ORDER[i] : i;      // expensive problems first (shorter tail), see b2_order_problems
         WppSolver<MT, NT> s(p, b, b2_smem);
         s.run();
     }
