@@ -250,6 +250,24 @@ def main():
     # device result of the host path equals the device path
     assert np.array_equal(host_it["u"], solver.get("u", B).cpu().numpy())
 
+    # ---------------- p50 latency of ONE problem (the reference's one-at-a-time use) ----------------
+    lat1 = None
+    if rank == 0:
+        s1 = BatchedMpcSolver(a.N, a.n_obst, a.tf, max_batch=1, device=local_rank, kernel=a.kernel)
+        one = {k: dev_t[k][:1].contiguous() for k in names_in + names_it}
+        for k in names_in:
+            s1.set(k, one[k])
+        lat = []
+        for i in range(60):
+            for k in names_it:
+                s1.set(k, one[k])
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); s1.solve(1); e1.record(stream); torch.cuda.synchronize(dev)
+            if i >= 10:
+                lat.append(e0.elapsed_time(e1))
+        lat1 = float(np.median(lat))
+        s1.close()
+
     # ---------------- reduce over ranks (max time; sum of work) ----------------
     sums, maxs = sharding.reduce_stats({"B": B, "qp_iter": float(qp_iter.sum()), "fail": float((status != 0).sum())},
                                        {"total_ms": total_ms, "e2e_s": e2e_s}, device=dev)
@@ -271,6 +289,13 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None                       # dram__bytes_read+write of the solve kernel, one ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("kernel") == solver.kernel_name and tr.get("batch") == B and (a.N, a.n_obst) == (tr.get("N"), tr.get("M")):
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -278,10 +303,10 @@ def main():
             "config": {"workload": workload_name(a), "global_batch": int(tot_B), "l2": "flushed between steps (256 MiB memset)",
                        "kernel": solver.kernel_name,
                        "parallelism": f"env-sharded x{world_size}, no data-path collective"},
-            "p50_latency_ms_per_batch": float(np.median(step_ms)),
+            "p50_latency_ms_per_batch": float(np.median(step_ms)), "p50_latency_ms_single_problem": lat1,
             "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "peak_source": "self-measured register-resident DFMA chains (b2mpc_dfma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 ~37-40 TFLOP/s",
                          "flops_per_launch": fl, "kernel_ms": kern_s * 1e3,
