@@ -30,7 +30,7 @@ __constant__ unsigned char B2_BATAB[5][7] = {
 };
 
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv;                  // used by the sweeps
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu;              // used by the sweeps
     int lam, t, tinv, dd;                                                       // per constraint (nct rows each); dd doubles as dlam
     int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrgsl, lrgsu, dsl, dsu, dli, dui, xu;
     int total;
@@ -39,7 +39,7 @@ struct WOff {
         const int nct = 12 + 4 * M;
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
-        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5;
+        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5; lu = o; o += 2;
         lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
         b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
         zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
@@ -556,7 +556,7 @@ struct WppSolver {
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double lu0 = w0 * l00i;
             const double lu1 = (w1 - l10 * lu0) * l11i;
-            if (lane == 0) { S(oDV + 0, kk) = lu0; S(oDV + 1, kk) = lu1; }
+            if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
             if (kk > 0) {
                 const double pa = (S(o.hg + 2 + c5, kk) + S(acol[0], kk) * s[0]) + (S(acol[1], kk) * s[1] + S(acol[2], kk) * s[2]);
                 const double pb = S(acol[3], kk) * s[3] + S(acol[4], kk) * s[4];
@@ -571,7 +571,7 @@ struct WppSolver {
         double dx[5] = {0, 0, 0, 0, 0};
         if (lane < 5) S(oDV + 2 + lane, 0) = 0.0;
         for (int kk = 0; kk < N; kk++) {
-            double r0 = S(oDV + 0, kk), r1 = S(oDV + 1, kk);
+            double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
             if (kk > 0) {
                 r0 = (r0 + S(o.lxu + 0, kk) * dx[0] + S(o.lxu + 2, kk) * dx[1]) + (S(o.lxu + 4, kk) * dx[2] + S(o.lxu + 6, kk) * dx[3] + S(o.lxu + 8, kk) * dx[4]);
                 r1 = (r1 + S(o.lxu + 1, kk) * dx[0] + S(o.lxu + 3, kk) * dx[1]) + (S(o.lxu + 5, kk) * dx[2] + S(o.lxu + 7, kk) * dx[3] + S(o.lxu + 9, kk) * dx[4]);
