@@ -17,6 +17,16 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libmpc_oracle.so")
+_LIB_PATH_V3 = os.path.join(_HERE, "_build", "libmpc_oracle_v3.so")
+
+
+def _cpu_has_v3() -> bool:
+    """x86-64-v3 build (AVX2/FMA/BMI2 code generation, FP contraction still off) only where the CPU has it"""
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+        return all(f in flags for f in ("avx2", "fma", "bmi2", "movbe"))
+    except Exception:
+        return False
 
 
 class OrcConfig(C.Structure):
@@ -43,8 +53,8 @@ def build(force: bool = False) -> str:
     """Compile oracle/mpc_oracle.c with gcc (recipe: oracle/Makefile)."""
     src = os.path.join(_HERE, "mpc_oracle.c")
     hdr = os.path.join(_HERE, "mpc_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in (src, hdr))
+    stale = any((not os.path.exists(lp)) or any(os.path.getmtime(f) > os.path.getmtime(lp) for f in (src, hdr))
+                for lp in (_LIB_PATH, _LIB_PATH_V3))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
@@ -59,7 +69,7 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(_LIB_PATH)
+        _lib = C.CDLL(_LIB_PATH_V3 if _cpu_has_v3() else _LIB_PATH)
         _lib.orc_rti_solve.restype = C.c_int
         _lib.orc_export_qp.restype = C.c_int
         _lib.orc_qp_solve_export.restype = C.c_int
