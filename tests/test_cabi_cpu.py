@@ -1,0 +1,69 @@
+"""CPU-side checks of the C-ABI (no GPU in this container): the shared library loads, exports every
+function declared in include/b200mpc.h, fills the reference defaults, validates arguments, and REFUSES to
+run without a CUDA device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from b200mpc import capi, build_ext
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_ext.build()
+    return capi.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200mpc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(b2mpc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/b200mpc.h but not exported"
+    assert set(capi.EXPORTS) <= names
+    assert lib.b2mpc_abi_version() == 1
+
+
+def test_default_config_matches_reference_constants(lib):
+    c = capi.default_config(20, 5, 2.0, 4096, 0)
+    assert (c.N, c.n_obst, c.max_batch, c.integrator, c.qp_iter_max) == (20, 5, 4096, 0, 50)
+    assert list(c.W) == [2, 2, 2, 2, 0.15, 0.15] and list(c.W_e) == [5, 5, 5, 5]          # robot_ocp_problem.py:24-27
+    assert list(c.lbx) == [-7, -7, -10, -10] and list(c.ubx) == [7, 7, 10, 10]            # :91-92
+    assert list(c.lbu) == [-8, -8] and list(c.ubu) == [8, 8] and c.lm == 2.0              # :95-96,128
+    assert abs(c.r2 - 2.4 ** 2) < 1e-15 and c.lh == 0.0 and c.uh == 1e5                   # robot_model.py:62, :99-103
+    assert (c.mu0, c.alpha_min, c.res_g_max, c.res_b_max) == (1.0, 1e-8, 1e-6, 1e-8)      # acados' HPIPM block
+    assert c.lm_scaled_by_dt == 1 and c.pred_corr == 1 and c.cond_pred_corr == 1 and c.itref_corr_max == 2
+
+
+def test_create_validates_arguments_and_has_no_cpu_fallback(lib):
+    import torch
+    h = C.c_void_p()
+    for bad in (dict(N=0), dict(N=129), dict(n_obst=0), dict(n_obst=33), dict(max_batch=0), dict(tf=0.0), dict(integrator=7)):
+        c = capi.default_config(20, 5, 2.0, 8, 0)
+        for k, v in bad.items():
+            setattr(c, k, v)
+        assert lib.b2mpc_create(C.byref(c), C.byref(h)) == -1          # B2MPC_EINVAL, before touching CUDA
+        assert lib.b2mpc_last_error()
+    if not torch.cuda.is_available():
+        c = capi.default_config(20, 5, 2.0, 8, 0)
+        rc = lib.b2mpc_create(C.byref(c), C.byref(h))
+        assert rc == -2 and b"no CUDA device" in lib.b2mpc_last_error()   # B2MPC_ENODEV: fails loudly
+        from b200mpc import BatchedMpcSolver
+        with pytest.raises(capi.B2mpcError):
+            BatchedMpcSolver(20, 5, 2.0, max_batch=8)
+        tf = C.c_double(0)
+        assert lib.b2mpc_dfma_peak(0, C.byref(tf)) == -2
+    assert lib.b2mpc_destroy(None) == 0
+    assert lib.b2mpc_field_len(None, 0) == -1
+
+
+def test_missing_library_is_a_loud_error(tmp_path, monkeypatch):
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(capi.B2mpcError):
+        capi.lib()
