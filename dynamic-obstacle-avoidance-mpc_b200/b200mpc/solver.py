@@ -154,7 +154,7 @@ class BatchedMpcSolver:
 
     @property
     def kernel_name(self):
-        return {1: "thread-per-problem", 2: "warp-per-problem"}[capi.lib().b2mpc_kernel(self._h)]
+        return {1: "thread-per-problem", 2: "warp-per-problem", 3: "warp-per-problem (all shared)"}[capi.lib().b2mpc_kernel(self._h)]
 
     @property
     def launch_count(self):

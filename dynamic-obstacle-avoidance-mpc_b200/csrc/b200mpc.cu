@@ -45,8 +45,15 @@ struct b2mpc {
     size_t stage_elems;
     int64_t launches;
     int32_t* order;                  // launch order for the warp kernel + 2 counters
-    int kernel;                      // resolved: 1 thread-per-problem, 2 warp-per-problem
+    int kernel;                      // resolved: 1 thread-per-problem, 2 warp-per-problem (hybrid layout), 3 warp-per-problem (all shared)
     size_t wpp_smem;
+    void (*wpp_fn)(const B2Params);  // selected instantiation of the warp kernel
+    int wpp_grid;                    // resident CTAs (SMs x occupancy): the persistent grid
+    double* wpriv;                   // node-private rows of the resident CTAs
+    size_t wpriv_bytes;
+    void (*wpp_fn_small)(const B2Params);   // auto mode: all-shared instantiation for batches that fit the GPU at once
+    size_t wpp_smem_small;
+    int small_batch_max;
     B2Params prm;
 };
 
@@ -151,32 +158,69 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         return fail(B2MPC_ENOMEM, "staging allocation failed");
     }
     fill_params(h);
-    // kernel selection: the warp-per-problem kernel keeps a whole problem on chip; it needs one lane
-    // per shooting node and its shared-memory block to fit one SM
-    h->wpp_smem = b2_wpp_smem_bytes(N, M);
+    // kernel selection.  The warp-per-problem kernel keeps the cross-lane part of a problem in shared
+    // memory; the node-private rows go to shared memory too (kernel 3, needs the whole problem to fit) or,
+    // per field, to an L2-resident block of global memory per resident CTA (kernel 2, any N <= 128).
+    unsigned smask = B2_WPP_ALL_GLOBAL;
+    h->wpp_fn = nullptr;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    const bool wpp_ok = (N + 1 <= 32) && (h->wpp_smem <= (size_t)max_smem);
-    if (cfg->kernel == 2 && !wpp_ok) {
-        b2mpc_destroy(h);
-        return fail(B2MPC_EINVAL, "warp-per-problem kernel needs N+1 <= 32 and %zu B <= %d B of shared memory", b2_wpp_smem_bytes(N, M), max_smem);
+    const bool ref_dims = (M == 5 && N == 20);          // the reference's configuration (world_specification.py:44-48)
+    const bool long_dims = (M == 20 && N == 100);       // BASELINE.json config 4
+    if (cfg->kernel == 3) {
+        smask = B2_WPP_ALL_SHARED;
+        if (b2_wpp_smem_bytes(N, M, smask) > (size_t)max_smem) {
+            b2mpc_destroy(h);
+            return fail(B2MPC_EINVAL, "all-shared warp kernel needs %zu B > %d B of shared memory", b2_wpp_smem_bytes(N, M, smask), max_smem);
+        }
+        h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED>;
+        h->kernel = 3;
+    } else if (cfg->kernel == 1) {
+        h->kernel = 1;
+    } else {
+        h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL>
+                  : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_ALL_GLOBAL> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
+        h->kernel = 2;
     }
-    h->kernel = (cfg->kernel == 1) ? 1 : (cfg->kernel == 2 ? 2 : (wpp_ok ? 2 : 1));
-    // global scratch is only needed by the thread-per-problem kernel (the warp kernel lives on chip)
+    // global scratch of the thread-per-problem kernel
     h->ws_bytes = h->kernel == 1 ? sizeof(double) * (size_t)B2Off(M).total * (N + 1) * h->Bm : 0;
     if (h->ws_bytes) {
         if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(workspace, %zu B) failed", h->ws_bytes); }
         cudaMemset(h->ws, 0, h->ws_bytes);
     }
     h->prm.WS = h->ws;
-    if (h->kernel == 2) {
-        if (cudaMalloc(&h->order, sizeof(int32_t) * ((size_t)h->Bm + 2)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
-    }
-    if (h->kernel == 2) {
-        cudaError_t e = (M == 5 && N == 20) ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
-                      : (M == 5)            ? cudaFuncSetAttribute(b2_rti_solve_wpp<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem)
-                                            : cudaFuncSetAttribute(b2_rti_solve_wpp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+    if (h->kernel != 1) {
+        h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
+        if (h->wpp_smem > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
+        if (cudaMalloc(&h->order, sizeof(int32_t) * ((size_t)h->Bm + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
+        cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+        int occ = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->wpp_fn, 32, h->wpp_smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (occ < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "warp kernel does not fit an SM"); }
+        h->wpp_grid = occ * sms;
+        if (h->wpp_grid > h->Bm) h->wpp_grid = h->Bm;
+        h->prm.wpriv_stride = b2_wpp_priv_doubles(N, M, smask);
+        h->wpriv_bytes = sizeof(double) * h->prm.wpriv_stride * (size_t)h->wpp_grid;
+        if (h->wpriv_bytes) {
+            if (cudaMalloc(&h->wpriv, h->wpriv_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(node-private rows, %zu B) failed", h->wpriv_bytes); }
+            cudaMemset(h->wpriv, 0, h->wpriv_bytes);
+        }
+        h->prm.WPRIV = h->wpriv;
+        // auto mode: a batch that fits the GPU in one wave of all-shared CTAs (<= 4 per SM at N=20, M=5) has no use
+        // for more resident CTAs, and the all-shared layout has the shorter per-problem latency (no L2 round trips):
+        // single closed-loop episodes (BASELINE config 1) and small batches take that instantiation.
+        if (cfg->kernel == 0 && b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED) <= (size_t)max_smem) {
+            h->wpp_fn_small = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED>;
+            h->wpp_smem_small = b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED);
+            int occ_s = 0;
+            if (cudaFuncSetAttribute(h->wpp_fn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem_small) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, h->wpp_fn_small, 32, h->wpp_smem_small) != cudaSuccess || occ_s < 1)
+                h->wpp_fn_small = nullptr;
+            h->small_batch_max = occ_s * sms;
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -190,6 +234,7 @@ extern "C" int b2mpc_destroy(b2mpc* h)
     for (int i = 0; i < B2MPC_N_FIELDS; i++) if (h->f[i]) cudaFree(h->f[i]);
     for (int i = 0; i < B2MPC_N_IFIELDS; i++) if (h->fi[i]) cudaFree(h->fi[i]);
     if (h->ws) cudaFree(h->ws);
+    if (h->wpriv) cudaFree(h->wpriv);
     if (h->order) cudaFree(h->order);
     if (h->stage_d) cudaFree(h->stage_d);
     if (h->stage_h) cudaFreeHost(h->stage_h);
@@ -203,7 +248,7 @@ extern "C" int64_t b2mpc_field_len(const b2mpc* h, int field)
     if (!h || field < 0 || field >= B2MPC_N_FIELDS) return -1;
     return h->len[field];
 }
-extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)h->ws_bytes : -1; }
+extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)(h->ws_bytes + h->wpriv_bytes) : -1; }
 extern "C" int64_t b2mpc_launch_count(const b2mpc* h) { return h ? h->launches : -1; }
 extern "C" int b2mpc_kernel(const b2mpc* h) { return h ? h->kernel : -1; }
 extern "C" double* b2mpc_field_ptr(b2mpc* h, int field)
@@ -611,17 +656,20 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     B2Params p = h->prm;
     p.B = (int)batch;
-    if (h->kernel == 2) {
-        int32_t* cnt = h->order + h->Bm;
-        CUDA_TRY(cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), st));
+    if (h->kernel != 1) {
+        int32_t* cnt = h->order + h->Bm;                 // [inside count, outside count, work counter]
+        CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * sizeof(int32_t), st));
         b2_order_problems<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], h->order, cnt, h->N, h->M,
                                                                          h->cfg.r2, (int)batch, h->Bm);
         h->launches++;
         p.ORDER = h->order;
-        const unsigned blocks = (unsigned)batch;          // one warp-CTA per problem
-        if (h->M == 5 && h->N == 20) b2_rti_solve_wpp<5, 20><<<blocks, 32, h->wpp_smem, st>>>(p);
-        else if (h->M == 5) b2_rti_solve_wpp<5, 0><<<blocks, 32, h->wpp_smem, st>>>(p);
-        else b2_rti_solve_wpp<0, 0><<<blocks, 32, h->wpp_smem, st>>>(p);
+        p.NEXT = cnt + 2;
+        if (h->wpp_fn_small && batch <= h->small_batch_max) {
+            h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
+        } else {
+            const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);   // persistent: one warp-CTA per resident slot
+            h->wpp_fn<<<blocks, 32, h->wpp_smem, st>>>(p);
+        }
     } else {
         const int threads = 64;
         const unsigned blocks = (unsigned)((batch + threads - 1) / threads);

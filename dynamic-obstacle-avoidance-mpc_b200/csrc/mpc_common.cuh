@@ -61,8 +61,11 @@ struct B2Params {
     double *PI, *LAM, *T, *STATS;
     int32_t *STATUS, *QP_ITER, *QP_STATUS;
     const int32_t* ORDER;        // optional launch order of the problems (warp kernel)
+    int32_t* NEXT;               // work counter of the persistent warp kernel (zeroed before each launch)
     // scratch
-    double* WS;
+    double* WS;                  // thread-per-problem kernel: all per-problem work arrays
+    double* WPRIV;               // warp kernel: node-private rows, one block of wpriv_stride doubles per resident CTA
+    size_t wpriv_stride;
 };
 
 // ---- products with S = [B A] (5 x 7), exploiting the generated sparsity pattern -------------

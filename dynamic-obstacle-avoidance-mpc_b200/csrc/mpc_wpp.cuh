@@ -9,9 +9,16 @@
 //   * the sequential backward/forward Riccati sweeps walk the nodes with the 7x7 node algebra
 //     spread over the lanes: lane e < 28 owns entry (i,j) of the symmetric Riccati matrix in the
 //     factorisation, lanes 0..6 own rows/columns in the vector sweeps; exchange by shuffles;
-//   * per-node data live in shared memory as rows [field][node]: lane==node accesses are
-//     conflict-free, the odd row stride keeps lane==field accesses conflict-free too.
-// One CTA = one warp = one problem at a time.
+//   * per-node data that other lanes read (model sensitivities, Riccati factors, steps, v, pi) live in
+//     shared memory as rows [field][node]: lane==node accesses are conflict-free, the odd row stride keeps
+//     lane==field accesses conflict-free too;
+//   * NODE-PRIVATE fields (multipliers, slacks of the inequality constraints and their steps, the QP's
+//     constraint data: only ever touched by the lane that owns the node) are addressed through Q<field>():
+//     the template mask SMASK places each field either in shared memory or in a per-CTA block of global
+//     memory (rows [field][node], coalesced, L2-resident: resident CTAs x ~40 KB).  Fewer shared-memory
+//     rows = more resident problems per SM, the lever that matters for this latency-bound kernel.
+//   * horizons with more than 32 nodes: a lane owns nodes lane, lane+32, ... (node-parallel phases loop).
+// One CTA = one warp = one problem at a time; CTAs are persistent and pull problems from a counter.
 //
 // Numerical note (why dlam is STORED and never re-derived): dlam_i = -(rm_i + lam_i dt_i)/t_i carries
 // lam/t up to ~1e18 on slack bounds, so iterative refinement only works if the correction is added
@@ -29,30 +36,56 @@ __constant__ unsigned char B2_BATAB[5][7] = {
     {11, 12, 11, 11, 11, 11, 10},
 };
 
+// node-private fields (see header): rows per field are nct for the first four, M for the obstacle fields
+enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD,                     // per constraint; dd doubles as dlam
+       PF_B, PF_G, PF_RG, PF_XU,                            // 5, 7, 7, 6 rows
+       PF_CX, PF_CY, PF_LG, PF_UG, PF_ZLQ, PF_ZZLQ, PF_SLI, PF_SUI, PF_SL, PF_SU,
+       PF_LRGSL, PF_LRGSU, PF_DSL, PF_DSU, PF_DLI, PF_DUI, PF_COUNT };
+#define B2_WPP_ALL_SHARED 0xffffffu
+// Placement used by default: EVERY node-private field in global memory.  Measured on B200 (N=20, M=5, 4096 problems,
+// profiles/experiments/r01_hybrid_layout.md): all global, 12 CTAs/SM 11.6 ms; lam,t shared, 7 CTAs/SM 13.1 ms;
+// lam,t,1/t,dlam shared, 5 CTAs/SM 14.3 ms; all shared, 4 CTAs/SM 12.7 ms.
+#define B2_WPP_ALL_GLOBAL 0u
+#ifndef B2_WPP_MINB
+#define B2_WPP_MINB 12          // resident CTAs per SM the N=20 layout is compiled for (register cap 65536/32/MINB = 170)
+#endif
+
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu;              // used by the sweeps
-    int lam, t, tinv, dd;                                                       // per constraint (nct rows each); dd doubles as dlam
-    int b, g, cx, cy, lg, ug, zlq, Zlq, sli, sui, v, sl, su, pi, rg, lrgsl, lrgsu, dsl, dsu, dli, dui, xu;
-    int total;
-    __host__ __device__ explicit WOff(int M)
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu, v, pi;       // shared-memory rows read across lanes
+    int pf[PF_COUNT];                                                           // row of each private field in ITS space
+    int total;                                                                  // shared-memory rows (incl. private fields placed there)
+    int gtotal;                                                                 // global-memory rows
+    __host__ __device__ static int pf_rows(int f, int M)
     {
-        const int nct = 12 + 4 * M;
+        return f <= PF_DD ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
+    }
+    __host__ __device__ WOff(int M, unsigned smask)
+    {
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
         cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5; lu = o; o += 2;
-        lam = o; o += nct; t = o; o += nct; tinv = o; o += nct; dd = o; o += nct;
-        b = o; o += 5; g = o; o += 7; cx = o; o += M; cy = o; o += M; lg = o; o += M; ug = o; o += M;
-        zlq = o; o += M; Zlq = o; o += M; sli = o; o += M; sui = o; o += M;
-        v = o; o += 7; sl = o; o += M; su = o; o += M; pi = o; o += 5; rg = o; o += 7;
-        lrgsl = o; o += M; lrgsu = o; o += M; dsl = o; o += M; dsu = o; o += M; dli = o; o += M; dui = o; o += M;
-        xu = o; o += 6;
+        v = o; o += 7; pi = o; o += 5;
+        int g = 0;
+        for (int f = 0; f < PF_COUNT; f++) {
+            if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M); }
+            else { pf[f] = g; g += pf_rows(f, M); }
+        }
         total = o;
+        gtotal = g;
     }
 };
 
-__host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd row stride
+__host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd shared-memory row stride
+__host__ __device__ inline int b2_wpp_gstride(int N) { return (N + 1 + 3) & ~3; }    // global row stride: 32 B sectors
 #define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
-__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M) { return sizeof(double) * ((size_t)WOff(M).total * b2_wpp_stride(N) + B2_WPP_SCRATCH); }
+__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned smask)
+{
+    return sizeof(double) * ((size_t)WOff(M, smask).total * b2_wpp_stride(N) + B2_WPP_SCRATCH);
+}
+__host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned smask)    // per resident CTA
+{
+    return (size_t)WOff(M, smask).gtotal * b2_wpp_gstride(N);
+}
 
 __device__ __forceinline__ double b2_warp_max(double v)
 {
@@ -71,23 +104,27 @@ __device__ __forceinline__ double b2_bcast(double v, int src) { return __shfl_sy
 // expansion modes
 enum { XP_SOLVE = 0, XP_REFINE = 1, XP_UPDATE = 2, XP_LIN = 3 };
 
-template <int MT, int NT>
+template <int MT, int NT, unsigned SMASK>
 struct WppSolver {
     const B2Params& p;
-    const int b, lane, N, NS, M, nct;
+    const int b, lane, N, NS, GS, M, nct;
     double* const sm;
+    double* const gm;
     const WOff o;
     const size_t Bm;
-    const int k;            // node owned by this lane
-    const bool act;
+    // obstacle loops stay rolled: unrolling them (more loads in flight per L2 round trip) was measured 40-70 %
+    // SLOWER -- the kernel is instruction-fetch sensitive (profiles/experiments/r01_hybrid_layout.md)
+    static constexpr int JU = 1;
+    int k;                  // node this lane is working on (node-parallel phases: lane, lane+32, ...)
     const int o_lb, o_lg, o_ub, o_ug, o_ls, o_us;
     int nc;
     double mu, nrm[4], sum_lt, alpha, S1, S2;
 
-    __device__ WppSolver(const B2Params& p_, int b_, double* sm_)
-        : p(p_), b(b_), lane(threadIdx.x & 31), N(NT > 0 ? NT : p_.N), NS(b2_wpp_stride(NT > 0 ? NT : p_.N)), M(MT > 0 ? MT : p_.M),
-          nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), o(MT > 0 ? MT : p_.M), Bm((size_t)p_.Bm),
-          k(threadIdx.x & 31), act((int)(threadIdx.x & 31) <= (NT > 0 ? NT : p_.N)),
+    __device__ WppSolver(const B2Params& p_, int b_, double* sm_, double* gm_)
+        : p(p_), b(b_), lane(threadIdx.x & 31), N(NT > 0 ? NT : p_.N), NS(b2_wpp_stride(NT > 0 ? NT : p_.N)),
+          GS(b2_wpp_gstride(NT > 0 ? NT : p_.N)), M(MT > 0 ? MT : p_.M),
+          nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), gm(gm_), o(MT > 0 ? MT : p_.M, SMASK), Bm((size_t)p_.Bm),
+          k(threadIdx.x & 31),
           o_lb(0), o_lg(6), o_ub(6 + (MT > 0 ? MT : p_.M)), o_ug(12 + (MT > 0 ? MT : p_.M)),
           o_ls(12 + 2 * (MT > 0 ? MT : p_.M)), o_us(12 + 3 * (MT > 0 ? MT : p_.M))
     {
@@ -96,11 +133,18 @@ struct WppSolver {
     }
 
     __device__ __forceinline__ double& S(int row, int kk) const { return sm[row * NS + kk]; }
+    // row i of private field F at the node this lane is working on
+    template <int F>
+    __device__ __forceinline__ double& Q(int i) const
+    {
+        if ((SMASK >> F) & 1u) return sm[(o.pf[F] + i) * NS + k];
+        return gm[(size_t)((o.pf[F] + i) * GS + k)];
+    }
     __device__ __forceinline__ bool box_on(int s, int kk) const { return s < 2 ? (kk < N) : (kk > 0 && kk < N); }
     __device__ __forceinline__ double scal(int kk) const { return kk < N ? p.dt : 1.0; }
     __device__ __forceinline__ void box_bounds(int s, double& lb, double& ub) const
     {
-        const double xv = S(o.xu + s, k);
+        const double xv = Q<PF_XU>(s);
         if (s < 2) { lb = p.lbu[s] - xv; ub = p.ubu[s] - xv; }
         else { lb = p.lbx[s - 2] - xv; ub = p.ubx[s - 2] - xv; }
     }
@@ -108,7 +152,7 @@ struct WppSolver {
     // ---- preparation + cold-start initialisation: lane k handles node k ----------------------------
     __device__ void prepare_and_init()
     {
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             double xk[5], uk[2] = {0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b];
@@ -121,33 +165,33 @@ struct WppSolver {
                 if (p.integrator == 1) model_rk4_step(xk, uk, p.dt, xn, sv);
                 else model_gl4_step(xk, uk, p.dt, xn, sv);
 #pragma unroll
-                for (int i = 0; i < 5; i++) S(o.b + i, k) = xn[i] - p.X[((size_t)(k + 1) * 5 + i) * Bm + b];
-                S(o.g + 0, k) = p.Wg[0] * (uk[0] - yr[4 * Bm]);
-                S(o.g + 1, k) = p.Wg[1] * (uk[1] - yr[5 * Bm]);
-                S(o.g + 2, k) = p.Wg[2] * (xk[0] - yr[0 * Bm]);
-                S(o.g + 3, k) = p.Wg[3] * (xk[1] - yr[1 * Bm]);
-                S(o.g + 4, k) = 0.0;
-                S(o.g + 5, k) = p.Wg[5] * (xk[3] - yr[2 * Bm]);
-                S(o.g + 6, k) = p.Wg[6] * (xk[4] - yr[3 * Bm]);
+                for (int i = 0; i < 5; i++) Q<PF_B>(i) = xn[i] - p.X[((size_t)(k + 1) * 5 + i) * Bm + b];
+                Q<PF_G>(0) = p.Wg[0] * (uk[0] - yr[4 * Bm]);
+                Q<PF_G>(1) = p.Wg[1] * (uk[1] - yr[5 * Bm]);
+                Q<PF_G>(2) = p.Wg[2] * (xk[0] - yr[0 * Bm]);
+                Q<PF_G>(3) = p.Wg[3] * (xk[1] - yr[1 * Bm]);
+                Q<PF_G>(4) = 0.0;
+                Q<PF_G>(5) = p.Wg[5] * (xk[3] - yr[2 * Bm]);
+                Q<PF_G>(6) = p.Wg[6] * (xk[4] - yr[3 * Bm]);
             } else {
-                S(o.g + 0, k) = 0.0; S(o.g + 1, k) = 0.0;
-                S(o.g + 2, k) = p.Wge[2] * (xk[0] - yr[0 * Bm]);
-                S(o.g + 3, k) = p.Wge[3] * (xk[1] - yr[1 * Bm]);
-                S(o.g + 4, k) = 0.0;
-                S(o.g + 5, k) = p.Wge[5] * (xk[3] - yr[2 * Bm]);
-                S(o.g + 6, k) = p.Wge[6] * (xk[4] - yr[3 * Bm]);
+                Q<PF_G>(0) = 0.0; Q<PF_G>(1) = 0.0;
+                Q<PF_G>(2) = p.Wge[2] * (xk[0] - yr[0 * Bm]);
+                Q<PF_G>(3) = p.Wge[3] * (xk[1] - yr[1 * Bm]);
+                Q<PF_G>(4) = 0.0;
+                Q<PF_G>(5) = p.Wge[5] * (xk[3] - yr[2 * Bm]);
+                Q<PF_G>(6) = p.Wge[6] * (xk[4] - yr[3 * Bm]);
             }
 #pragma unroll
             for (int i = 0; i < 10; i++) S(o.sv + i, k) = sv[i];
             S(o.sv + 10, k) = 1.0; S(o.sv + 11, k) = 0.0; S(o.sv + 12, k) = p.dt; S(o.sv + 13, k) = p.dt2h;
-            S(o.xu + 0, k) = uk[0]; S(o.xu + 1, k) = uk[1];
-            S(o.xu + 2, k) = xk[0]; S(o.xu + 3, k) = xk[1]; S(o.xu + 4, k) = xk[3]; S(o.xu + 5, k) = xk[4];
+            Q<PF_XU>(0) = uk[0]; Q<PF_XU>(1) = uk[1];
+            Q<PF_XU>(2) = xk[0]; Q<PF_XU>(3) = xk[1]; Q<PF_XU>(4) = xk[3]; Q<PF_XU>(5) = xk[4];
             double v[7] = {0, 0, 0, 0, 0, 0, 0};
             if (k == 0) {
 #pragma unroll
                 for (int i = 0; i < 5; i++) v[2 + i] = p.X0[(size_t)i * Bm + b] - xk[i];
             }
-            for (int i = 0; i < nct; i++) { S(o.lam + i, k) = 0.0; S(o.t + i, k) = 0.0; S(o.tinv + i, k) = 0.0; S(o.dd + i, k) = 0.0; }
+            for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; }
 #pragma unroll
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
@@ -159,29 +203,29 @@ struct WppSolver {
                     if (tu < p.thr0) { v[iv] = 0.5 * (lb + ub); tl = p.thr0; tu = p.thr0; }
                     else { tl = p.thr0; v[iv] = lb + p.thr0; }
                 } else if (tu < p.thr0) { tu = p.thr0; v[iv] = ub - p.thr0; }
-                S(o.t + o_lb + s, k) = tl; S(o.t + o_ub + s, k) = tu;
-                S(o.lam + o_lb + s, k) = p.mu0 / tl; S(o.lam + o_ub + s, k) = p.mu0 / tu;
+                Q<PF_T>(o_lb + s) = tl; Q<PF_T>(o_ub + s) = tu;
+                Q<PF_LAM>(o_lb + s) = p.mu0 / tl; Q<PF_LAM>(o_ub + s) = p.mu0 / tu;
             }
-#pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
                 double hval, cx, cy;
                 model_con_h(xk, p.P[((size_t)k * 2 * M + 2 * j) * Bm + b], p.P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b], p.r2, &hval, &cx, &cy);
                 const double s_l = p.SL[((size_t)k * M + j) * Bm + b], s_u = p.SU[((size_t)k * M + j) * Bm + b];
                 const double lg = p.lh - hval - s_l, ug = p.uh - hval + s_u;
-                S(o.cx + j, k) = cx; S(o.cy + j, k) = cy; S(o.lg + j, k) = lg; S(o.ug + j, k) = ug;
-                S(o.sli + j, k) = s_l; S(o.sui + j, k) = s_u;
+                Q<PF_CX>(j) = cx; Q<PF_CY>(j) = cy; Q<PF_LG>(j) = lg; Q<PF_UG>(j) = ug;
+                Q<PF_SLI>(j) = s_l; Q<PF_SUI>(j) = s_u;
                 const double zl_in = p.ZL[((size_t)k * M + j) * Bm + b], Zl_in = p.ZZL[((size_t)k * M + j) * Bm + b];
-                S(o.zlq + j, k) = sc * (zl_in + Zl_in * s_l);
-                S(o.Zlq + j, k) = sc * Zl_in;
+                Q<PF_ZLQ>(j) = sc * (zl_in + Zl_in * s_l);
+                Q<PF_ZZLQ>(j) = sc * Zl_in;
                 const double cv = cx * v[2] + cy * v[3];
                 double tl = cv - lg, tu = ug - cv;
                 tl = p.thr0 > tl ? p.thr0 : tl;
                 tu = p.thr0 > tu ? p.thr0 : tu;
-                S(o.t + o_lg + j, k) = tl; S(o.t + o_ug + j, k) = tu;
-                S(o.lam + o_lg + j, k) = p.mu0 / tl; S(o.lam + o_ug + j, k) = p.mu0 / tu;
-                S(o.t + o_ls + j, k) = 1.0; S(o.t + o_us + j, k) = 1.0;
-                S(o.lam + o_ls + j, k) = p.mu0; S(o.lam + o_us + j, k) = p.mu0;
-                S(o.sl + j, k) = 0.0; S(o.su + j, k) = 0.0;
+                Q<PF_T>(o_lg + j) = tl; Q<PF_T>(o_ug + j) = tu;
+                Q<PF_LAM>(o_lg + j) = p.mu0 / tl; Q<PF_LAM>(o_ug + j) = p.mu0 / tu;
+                Q<PF_T>(o_ls + j) = 1.0; Q<PF_T>(o_us + j) = 1.0;
+                Q<PF_LAM>(o_ls + j) = p.mu0; Q<PF_LAM>(o_us + j) = p.mu0;
+                Q<PF_SL>(j) = 0.0; Q<PF_SU>(j) = 0.0;
             }
 #pragma unroll
             for (int i = 0; i < 7; i++) S(o.v + i, k) = v[i];
@@ -199,12 +243,12 @@ struct WppSolver {
     __device__ void residuals()
     {
         double sum = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             double v[7], rg[7];
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
 #pragma unroll
-            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + S(o.g + i, k); }
+            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); }
             double sv[10];
             if (k < N) {
 #pragma unroll
@@ -224,8 +268,8 @@ struct WppSolver {
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
                 const int iv = b2_slot2v(s);
-                const double ll = S(o.lam + o_lb + s, k), lu_ = S(o.lam + o_ub + s, k);
-                const double tl = S(o.t + o_lb + s, k), tu = S(o.t + o_ub + s, k);
+                const double ll = Q<PF_LAM>(o_lb + s), lu_ = Q<PF_LAM>(o_ub + s);
+                const double tl = Q<PF_T>(o_lb + s), tu = Q<PF_T>(o_ub + s);
                 rg[iv] += -ll + lu_;
                 const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
                 n2 = fmax(n2, fmax(fabs(rdl), fabs(rdu)));
@@ -234,21 +278,21 @@ struct WppSolver {
                 sum += ml; sum += mu_;
             }
             const double Zuq = sc * p.Zu;
-#pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
-                const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+                const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
                 const double cv = cx * v[2] + cy * v[3];
-                const double llg = S(o.lam + o_lg + j, k), lug = S(o.lam + o_ug + j, k), lls = S(o.lam + o_ls + j, k), lus = S(o.lam + o_us + j, k);
-                const double tlg = S(o.t + o_lg + j, k), tug = S(o.t + o_ug + j, k), tls = S(o.t + o_ls + j, k), tus = S(o.t + o_us + j, k);
+                const double llg = Q<PF_LAM>(o_lg + j), lug = Q<PF_LAM>(o_ug + j), lls = Q<PF_LAM>(o_ls + j), lus = Q<PF_LAM>(o_us + j);
+                const double tlg = Q<PF_T>(o_lg + j), tug = Q<PF_T>(o_ug + j), tls = Q<PF_T>(o_ls + j), tus = Q<PF_T>(o_us + j);
                 const double dl = lug - llg;
                 rg[2] += cx * dl; rg[3] += cy * dl;
-                const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
-                const double sli = S(o.sli + j, k), sui = S(o.sui + j, k);
-                const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - llg - lls;
+                const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
+                const double sli = Q<PF_SLI>(j), sui = Q<PF_SUI>(j);
+                const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - llg - lls;
                 const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * sui) - lug - lus;
                 n0 = fmax(n0, fmax(fabs(rgsl), fabs(rgsu)));
-                const double rdlg = cv + s_l - S(o.lg + j, k) - tlg;
-                const double rdug = S(o.ug + j, k) - cv + s_u - tug;
+                const double rdlg = cv + s_l - Q<PF_LG>(j) - tlg;
+                const double rdug = Q<PF_UG>(j) - cv + s_u - tug;
                 const double rdls = s_l + sli - tls;
                 const double rdus = s_u + sui - tus;
                 n2 = fmax(n2, fmax(fmax(fabs(rdlg), fabs(rdug)), fmax(fabs(rdls), fabs(rdus))));
@@ -261,7 +305,7 @@ struct WppSolver {
                 b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
-                    rb[i] += S(o.b + i, k) - S(o.v + 2 + i, k + 1);
+                    rb[i] += Q<PF_B>(i) - S(o.v + 2 + i, k + 1);
                     S(o.rb + i, k) = rb[i];
                     n1 = fmax(n1, fabs(rb[i]));
                 }
@@ -269,7 +313,7 @@ struct WppSolver {
             if (k == 0) { rg[2] = rg[3] = rg[4] = rg[5] = rg[6] = 0.0; }
             if (k == N) { rg[0] = rg[1] = 0.0; }
 #pragma unroll
-            for (int i = 0; i < 7; i++) { S(o.rg + i, k) = rg[i]; n0 = fmax(n0, fabs(rg[i])); }
+            for (int i = 0; i < 7; i++) { Q<PF_RG>(i) = rg[i]; n0 = fmax(n0, fabs(rg[i])); }
         }
         sum = b2_warp_sum(sum);
         nrm[0] = b2_warp_max(n0); nrm[1] = b2_warp_max(n1); nrm[2] = b2_warp_max(n2); nrm[3] = b2_warp_max(n3);
@@ -281,7 +325,7 @@ struct WppSolver {
     // ---- barrier/slack elimination -> condensed node Hessians (lane k), then the Riccati recursion ---
     __device__ void factorize()
     {
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
             double Hx[7], hxy = 0.0;
@@ -290,23 +334,23 @@ struct WppSolver {
 #pragma unroll
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
-                const double til = 1.0 / S(o.t + o_lb + s, k), tiu = 1.0 / S(o.t + o_ub + s, k);
-                S(o.tinv + o_lb + s, k) = til; S(o.tinv + o_ub + s, k) = tiu;
-                Hx[b2_slot2v(s)] += S(o.lam + o_lb + s, k) * til + S(o.lam + o_ub + s, k) * tiu;
+                const double til = 1.0 / Q<PF_T>(o_lb + s), tiu = 1.0 / Q<PF_T>(o_ub + s);
+                Q<PF_TINV>(o_lb + s) = til; Q<PF_TINV>(o_ub + s) = tiu;
+                Hx[b2_slot2v(s)] += Q<PF_LAM>(o_lb + s) * til + Q<PF_LAM>(o_ub + s) * tiu;
             }
             const double Zuq = sc * p.Zu;
-#pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
-                const double t0 = 1.0 / S(o.t + o_lg + j, k), t1 = 1.0 / S(o.t + o_ug + j, k);
-                const double t2 = 1.0 / S(o.t + o_ls + j, k), t3 = 1.0 / S(o.t + o_us + j, k);
-                S(o.tinv + o_lg + j, k) = t0; S(o.tinv + o_ug + j, k) = t1; S(o.tinv + o_ls + j, k) = t2; S(o.tinv + o_us + j, k) = t3;
-                const double Gl = S(o.lam + o_lg + j, k) * t0, Gu = S(o.lam + o_ug + j, k) * t1;
-                const double Gls = S(o.lam + o_ls + j, k) * t2, Gus = S(o.lam + o_us + j, k) * t3;
-                const double Zlq = S(o.Zlq + j, k);
+                const double t0 = 1.0 / Q<PF_T>(o_lg + j), t1 = 1.0 / Q<PF_T>(o_ug + j);
+                const double t2 = 1.0 / Q<PF_T>(o_ls + j), t3 = 1.0 / Q<PF_T>(o_us + j);
+                Q<PF_TINV>(o_lg + j) = t0; Q<PF_TINV>(o_ug + j) = t1; Q<PF_TINV>(o_ls + j) = t2; Q<PF_TINV>(o_us + j) = t3;
+                const double Gl = Q<PF_LAM>(o_lg + j) * t0, Gu = Q<PF_LAM>(o_ug + j) * t1;
+                const double Gls = Q<PF_LAM>(o_ls + j) * t2, Gus = Q<PF_LAM>(o_us + j) * t3;
+                const double Zlq = Q<PF_ZZLQ>(j);
                 const double Dli = 1.0 / (Zlq + Gl + Gls), Dui = 1.0 / (Zuq + Gu + Gus);
-                S(o.dli + j, k) = Dli; S(o.dui + j, k) = Dui;
+                Q<PF_DLI>(j) = Dli; Q<PF_DUI>(j) = Dui;
                 const double weff = Gl * (Zlq + Gls) * Dli + Gu * (Zuq + Gus) * Dui;
-                const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+                const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
                 Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
             }
 #pragma unroll
@@ -411,11 +455,13 @@ struct WppSolver {
         }
     }
 
-    __device__ __forceinline__ double rm_of(int kind, double l, double t, double dd, double smu) const
+    // complementarity right-hand side of a base solve: kind 0 (affine) lam t; 1 (corrector) lam t + dt_aff dlam_aff - sigma mu;
+    // 2 (centering) lam t - sigma mu.  Branch-free in the run-time kind: rm_cdd = [kind == 1], rm_smu = kind ? sigma mu : 0
+    // (set by solve_any), evaluated as fma(lam, t, rm_cdd * dd) - rm_smu.
+    double rm_cdd, rm_smu;
+    __device__ __forceinline__ double rm_of(int, double l, double t, double dd, double) const
     {
-        if (kind == 0) return l * t;
-        if (kind == 1) return l * t + dd - smu;
-        return l * t - smu;
+        return (l * t + rm_cdd * dd) - rm_smu;
     }
 
     // q_lg, q_ug and the slack-elimination right-hand sides rho_l, rho_u of obstacle j at node k, base kinds
@@ -423,20 +469,20 @@ struct WppSolver {
                                               double& rhol, double& rhou, double& q0, double& q1) const
     {
         const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
-        const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
-        const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
-        const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
-        const double cv = S(o.cx + j, k) * v[2] + S(o.cy + j, k) * v[3];
-        const double rd0 = cv + s_l - S(o.lg + j, k) - t0;
-        const double rd1 = S(o.ug + j, k) - cv + s_u - t1;
-        const double rd2 = s_l + S(o.sli + j, k) - t2;
-        const double rd3 = s_u + S(o.sui + j, k) - t3;
-        q0 = (rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * rd0) * S(o.tinv + i0, k);
-        q1 = (rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * rd1) * S(o.tinv + i1, k);
-        const double q2 = (rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * rd2) * S(o.tinv + i2, k);
-        const double q3 = (rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * rd3) * S(o.tinv + i3, k);
-        const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
-        const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
+        const double l0 = Q<PF_LAM>(i0), l1 = Q<PF_LAM>(i1), l2 = Q<PF_LAM>(i2), l3 = Q<PF_LAM>(i3);
+        const double t0 = Q<PF_T>(i0), t1 = Q<PF_T>(i1), t2 = Q<PF_T>(i2), t3 = Q<PF_T>(i3);
+        const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
+        const double cv = Q<PF_CX>(j) * v[2] + Q<PF_CY>(j) * v[3];
+        const double rd0 = cv + s_l - Q<PF_LG>(j) - t0;
+        const double rd1 = Q<PF_UG>(j) - cv + s_u - t1;
+        const double rd2 = s_l + Q<PF_SLI>(j) - t2;
+        const double rd3 = s_u + Q<PF_SUI>(j) - t3;
+        q0 = (rm_of(kind, l0, t0, Q<PF_DD>(i0), smu) + l0 * rd0) * Q<PF_TINV>(i0);
+        q1 = (rm_of(kind, l1, t1, Q<PF_DD>(i1), smu) + l1 * rd1) * Q<PF_TINV>(i1);
+        const double q2 = (rm_of(kind, l2, t2, Q<PF_DD>(i2), smu) + l2 * rd2) * Q<PF_TINV>(i2);
+        const double q3 = (rm_of(kind, l3, t3, Q<PF_DD>(i3), smu) + l3 * rd3) * Q<PF_TINV>(i3);
+        const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - l0 - l2;
+        const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * Q<PF_SUI>(j)) - l1 - l3;
         rhol = rgsl + q0 + q2;
         rhou = rgsu + q1 + q3;
     }
@@ -445,42 +491,42 @@ struct WppSolver {
     // (0 affine, 1 corrector, 2 centering, 3 refinement = linear residual) -> rows hg[0..6]
     __device__ void solve_prep(int kind, double smu)
     {
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             const double sc = scal(k);
             double gt[7];
             if (kind == 3) {
 #pragma unroll
                 for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, k);          // lin_residuals left lrg here
-    #pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
-                    const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
-                    const double coef = -G0 * S(o.lrgsl + j, k) * S(o.dli + j, k) + G1 * S(o.lrgsu + j, k) * S(o.dui + j, k);
-                    gt[2] += S(o.cx + j, k) * coef;
-                    gt[3] += S(o.cy + j, k) * coef;
+                    const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
+                    const double coef = -G0 * Q<PF_LRGSL>(j) * Q<PF_DLI>(j) + G1 * Q<PF_LRGSU>(j) * Q<PF_DUI>(j);
+                    gt[2] += Q<PF_CX>(j) * coef;
+                    gt[3] += Q<PF_CY>(j) * coef;
                 }
             } else {
                 double v[7];
 #pragma unroll
-                for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = S(o.rg + i, k); }
+                for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = Q<PF_RG>(i); }
 #pragma unroll
                 for (int s = 0; s < 6; s++) {
                     if (!box_on(s, k)) continue;
                     const int il = o_lb + s, iu = o_ub + s;
-                    const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
+                    const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
                     const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
-                    const double ql = (rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * rdl) * S(o.tinv + il, k);
-                    const double qu = (rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * rdu) * S(o.tinv + iu, k);
+                    const double ql = (rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * rdl) * Q<PF_TINV>(il);
+                    const double qu = (rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * rdu) * Q<PF_TINV>(iu);
                     gt[b2_slot2v(s)] += ql - qu;
                 }
                 const double Zuq = sc * p.Zu;
-    #pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
                     double rhol, rhou, q0, q1;
                     slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
-                    const double G0 = S(o.lam + o_lg + j, k) * S(o.tinv + o_lg + j, k), G1 = S(o.lam + o_ug + j, k) * S(o.tinv + o_ug + j, k);
-                    const double coef = (q0 - G0 * rhol * S(o.dli + j, k)) - (q1 - G1 * rhou * S(o.dui + j, k));
-                    gt[2] += S(o.cx + j, k) * coef;
-                    gt[3] += S(o.cy + j, k) * coef;
+                    const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
+                    const double coef = (q0 - G0 * rhol * Q<PF_DLI>(j)) - (q1 - G1 * rhou * Q<PF_DUI>(j));
+                    gt[2] += Q<PF_CX>(j) * coef;
+                    gt[3] += Q<PF_CY>(j) * coef;
                 }
             }
 #pragma unroll
@@ -522,7 +568,7 @@ struct WppSolver {
     {
         const bool itr = (kind == 3);
         const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.dv, oDPI = itr ? o.cpi : o.dpi;
-        if (act && k < N) {
+        for (k = lane; k < N; k += 32) {
             double rb[5], z[5];
 #pragma unroll
             for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
@@ -588,7 +634,7 @@ struct WppSolver {
         }
         if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
         __syncwarp();
-        if (act && k < N) {
+        for (k = lane; k < N; k += 32) {
             double dxn[5], y[5];
 #pragma unroll
             for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
@@ -630,84 +676,84 @@ struct WppSolver {
             if (!box_on(s, k)) continue;
             const int iv = b2_slot2v(s);
             const int il = o_lb + s, iu = o_ub + s;
-            const double ll = S(o.lam + il, k), lu_ = S(o.lam + iu, k), tl = S(o.t + il, k), tu = S(o.t + iu, k);
+            const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
             const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
             const double dtl = dv[iv] + rdl, dtu = -dv[iv] + rdu;
             double dll, dlu;
             if (MODE == XP_SOLVE) {
-                dll = -(rm_of(kind, ll, tl, S(o.dd + il, k), smu) + ll * dtl) * S(o.tinv + il, k);
-                dlu = -(rm_of(kind, lu_, tu, S(o.dd + iu, k), smu) + lu_ * dtu) * S(o.tinv + iu, k);
-                S(o.dd + il, k) = keep_dd ? dtl * dll : dll;
-                S(o.dd + iu, k) = keep_dd ? dtu * dlu : dlu;
+                dll = -(rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * dtl) * Q<PF_TINV>(il);
+                dlu = -(rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * dtu) * Q<PF_TINV>(iu);
+                Q<PF_DD>(il) = keep_dd ? dtl * dll : dll;
+                Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
             } else if (MODE == XP_REFINE) {
-                dll = S(o.dd + il, k) - ll * cv[iv] * S(o.tinv + il, k);
-                dlu = S(o.dd + iu, k) + lu_ * cv[iv] * S(o.tinv + iu, k);
-                S(o.dd + il, k) = dll; S(o.dd + iu, k) = dlu;
+                dll = Q<PF_DD>(il) - ll * cv[iv] * Q<PF_TINV>(il);
+                dlu = Q<PF_DD>(iu) + lu_ * cv[iv] * Q<PF_TINV>(iu);
+                Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
             } else {
-                dll = S(o.dd + il, k); dlu = S(o.dd + iu, k);
+                dll = Q<PF_DD>(il); dlu = Q<PF_DD>(iu);
             }
             consume<MODE>(il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
             consume<MODE>(iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
             if (MODE == XP_LIN) lrg[iv] += -dll + dlu;
         }
-#pragma unroll 1
+#pragma unroll JU
         for (int j = 0; j < M; j++) {
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
-            const double cx = S(o.cx + j, k), cy = S(o.cy + j, k);
+            const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
             const double cdv = cx * dv[2] + cy * dv[3];
-            const double l0 = S(o.lam + i0, k), l1 = S(o.lam + i1, k), l2 = S(o.lam + i2, k), l3 = S(o.lam + i3, k);
-            const double t0 = S(o.t + i0, k), t1 = S(o.t + i1, k), t2 = S(o.t + i2, k), t3 = S(o.t + i3, k);
-            const double s_l = S(o.sl + j, k), s_u = S(o.su + j, k);
+            const double l0 = Q<PF_LAM>(i0), l1 = Q<PF_LAM>(i1), l2 = Q<PF_LAM>(i2), l3 = Q<PF_LAM>(i3);
+            const double t0 = Q<PF_T>(i0), t1 = Q<PF_T>(i1), t2 = Q<PF_T>(i2), t3 = Q<PF_T>(i3);
+            const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
             const double cval = cx * v[2] + cy * v[3];
-            const double rd0 = cval + s_l - S(o.lg + j, k) - t0;
-            const double rd1 = S(o.ug + j, k) - cval + s_u - t1;
-            const double rd2 = s_l + S(o.sli + j, k) - t2;
-            const double rd3 = s_u + S(o.sui + j, k) - t3;
+            const double rd0 = cval + s_l - Q<PF_LG>(j) - t0;
+            const double rd1 = Q<PF_UG>(j) - cval + s_u - t1;
+            const double rd2 = s_l + Q<PF_SLI>(j) - t2;
+            const double rd3 = s_u + Q<PF_SUI>(j) - t3;
             double dsl, dsu, dl0, dl1, dl2, dl3;
             if (MODE == XP_SOLVE) {
-                const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
+                const double ti0 = Q<PF_TINV>(i0), ti1 = Q<PF_TINV>(i1), ti2 = Q<PF_TINV>(i2), ti3 = Q<PF_TINV>(i3);
                 double rhol, rhou, q0, q1;
                 slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
-                dsl = -(l0 * ti0 * cdv + rhol) * S(o.dli + j, k);
-                dsu = -(-l1 * ti1 * cdv + rhou) * S(o.dui + j, k);
-                S(o.dsl + j, k) = dsl; S(o.dsu + j, k) = dsu;
+                dsl = -(l0 * ti0 * cdv + rhol) * Q<PF_DLI>(j);
+                dsu = -(-l1 * ti1 * cdv + rhou) * Q<PF_DUI>(j);
+                Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu;
                 const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
-                dl0 = -(rm_of(kind, l0, t0, S(o.dd + i0, k), smu) + l0 * dt0) * ti0;
-                dl1 = -(rm_of(kind, l1, t1, S(o.dd + i1, k), smu) + l1 * dt1) * ti1;
-                dl2 = -(rm_of(kind, l2, t2, S(o.dd + i2, k), smu) + l2 * dt2) * ti2;
-                dl3 = -(rm_of(kind, l3, t3, S(o.dd + i3, k), smu) + l3 * dt3) * ti3;
-                S(o.dd + i0, k) = keep_dd ? dt0 * dl0 : dl0; S(o.dd + i1, k) = keep_dd ? dt1 * dl1 : dl1;
-                S(o.dd + i2, k) = keep_dd ? dt2 * dl2 : dl2; S(o.dd + i3, k) = keep_dd ? dt3 * dl3 : dl3;
+                dl0 = -(rm_of(kind, l0, t0, Q<PF_DD>(i0), smu) + l0 * dt0) * ti0;
+                dl1 = -(rm_of(kind, l1, t1, Q<PF_DD>(i1), smu) + l1 * dt1) * ti1;
+                dl2 = -(rm_of(kind, l2, t2, Q<PF_DD>(i2), smu) + l2 * dt2) * ti2;
+                dl3 = -(rm_of(kind, l3, t3, Q<PF_DD>(i3), smu) + l3 * dt3) * ti3;
+                Q<PF_DD>(i0) = keep_dd ? dt0 * dl0 : dl0; Q<PF_DD>(i1) = keep_dd ? dt1 * dl1 : dl1;
+                Q<PF_DD>(i2) = keep_dd ? dt2 * dl2 : dl2; Q<PF_DD>(i3) = keep_dd ? dt3 * dl3 : dl3;
             } else if (MODE == XP_REFINE) {
-                const double ti0 = S(o.tinv + i0, k), ti1 = S(o.tinv + i1, k), ti2 = S(o.tinv + i2, k), ti3 = S(o.tinv + i3, k);
+                const double ti0 = Q<PF_TINV>(i0), ti1 = Q<PF_TINV>(i1), ti2 = Q<PF_TINV>(i2), ti3 = Q<PF_TINV>(i3);
                 const double ccv = cx * cv[2] + cy * cv[3];
-                const double csl = -(l0 * ti0 * ccv + S(o.lrgsl + j, k)) * S(o.dli + j, k);
-                const double csu = -(-l1 * ti1 * ccv + S(o.lrgsu + j, k)) * S(o.dui + j, k);
-                dsl = S(o.dsl + j, k) + csl; dsu = S(o.dsu + j, k) + csu;
-                S(o.dsl + j, k) = dsl; S(o.dsu + j, k) = dsu;
-                dl0 = S(o.dd + i0, k) - l0 * (ccv + csl) * ti0;
-                dl1 = S(o.dd + i1, k) - l1 * (-ccv + csu) * ti1;
-                dl2 = S(o.dd + i2, k) - l2 * csl * ti2;
-                dl3 = S(o.dd + i3, k) - l3 * csu * ti3;
-                S(o.dd + i0, k) = dl0; S(o.dd + i1, k) = dl1; S(o.dd + i2, k) = dl2; S(o.dd + i3, k) = dl3;
+                const double csl = -(l0 * ti0 * ccv + Q<PF_LRGSL>(j)) * Q<PF_DLI>(j);
+                const double csu = -(-l1 * ti1 * ccv + Q<PF_LRGSU>(j)) * Q<PF_DUI>(j);
+                dsl = Q<PF_DSL>(j) + csl; dsu = Q<PF_DSU>(j) + csu;
+                Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu;
+                dl0 = Q<PF_DD>(i0) - l0 * (ccv + csl) * ti0;
+                dl1 = Q<PF_DD>(i1) - l1 * (-ccv + csu) * ti1;
+                dl2 = Q<PF_DD>(i2) - l2 * csl * ti2;
+                dl3 = Q<PF_DD>(i3) - l3 * csu * ti3;
+                Q<PF_DD>(i0) = dl0; Q<PF_DD>(i1) = dl1; Q<PF_DD>(i2) = dl2; Q<PF_DD>(i3) = dl3;
             } else {
-                dsl = S(o.dsl + j, k); dsu = S(o.dsu + j, k);
-                dl0 = S(o.dd + i0, k); dl1 = S(o.dd + i1, k); dl2 = S(o.dd + i2, k); dl3 = S(o.dd + i3, k);
+                dsl = Q<PF_DSL>(j); dsu = Q<PF_DSU>(j);
+                dl0 = Q<PF_DD>(i0); dl1 = Q<PF_DD>(i1); dl2 = Q<PF_DD>(i2); dl3 = Q<PF_DD>(i3);
             }
             const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
             consume<MODE>(i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
             consume<MODE>(i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
             consume<MODE>(i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
             consume<MODE>(i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
-            if (MODE == XP_UPDATE) { S(o.sl + j, k) = s_l + a * dsl; S(o.su + j, k) = s_u + a * dsu; }
+            if (MODE == XP_UPDATE) { Q<PF_SL>(j) = s_l + a * dsl; Q<PF_SU>(j) = s_u + a * dsu; }
             if (MODE == XP_LIN) {
                 const double dl = dl1 - dl0;
                 lrg[2] += cx * dl; lrg[3] += cy * dl;
-                const double rgsl = S(o.Zlq + j, k) * s_l + S(o.zlq + j, k) - l0 - l2;
-                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * S(o.sui + j, k)) - l1 - l3;
-                const double a0 = S(o.Zlq + j, k) * dsl + rgsl - dl0 - dl2;
+                const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - l0 - l2;
+                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * Q<PF_SUI>(j)) - l1 - l3;
+                const double a0 = Q<PF_ZZLQ>(j) * dsl + rgsl - dl0 - dl2;
                 const double a1 = Zuq * dsu + rgsu - dl1 - dl3;
-                S(o.lrgsl + j, k) = a0; S(o.lrgsu + j, k) = a1;
+                Q<PF_LRGSL>(j) = a0; Q<PF_LRGSU>(j) = a1;
                 ln0 = fmax(ln0, fmax(fabs(a0), fabs(a1)));
             }
         }
@@ -731,7 +777,7 @@ struct WppSolver {
             double ln = l + a * dli, tn = t + a * dti;
             if (ln <= p.lam_min) ln = p.lam_min;
             if (tn <= p.t_min) tn = p.t_min;
-            S(o.lam + i, k) = ln; S(o.t + i, k) = tn;
+            Q<PF_LAM>(i) = ln; Q<PF_T>(i) = tn;
         }
     }
 
@@ -743,27 +789,24 @@ struct WppSolver {
         alpha = -(ap > ad ? ap : ad);
     }
 
-    // solve for a base right-hand side (0 affine, 1 corrector, 2 centering) + step-length reductions
-    __device__ void solve_base(int kind, double smu)
+    // One linear solve with the current factorisation + step-length reductions.  kind 0 affine, 1 corrector,
+    // 2 centering: base right-hand sides; kind 3: one iterative-refinement step (solve for the linear residual
+    // and add the correction).  `kind` is a RUN-TIME value and run() has a single call site: every phase of the
+    // interior-point iteration exists once in the instruction stream (the kernel is instruction-fetch
+    // sensitive: many warps per SM, each at its own place in a long straight-line program).
+    __device__ __forceinline__ void solve_any(int kind, double smu)
     {
+        rm_cdd = kind == 1 ? 1.0 : 0.0;
+        rm_smu = kind == 0 ? 0.0 : smu;
         solve_prep(kind, smu);
         riccati_solve(kind);
         double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
         ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
-        if (act) expand<XP_SOLVE>(kind, smu, 0.0, ap, ad, s1, s2, nullptr, dummy);
-        ap = ap_n / ap_d; ad = ad_n / ad_d;
-        reduce_step_length(ap, ad, s1, s2);
-        __syncwarp();
-    }
-
-    // one iterative-refinement step: solve for the linear residual and add the correction
-    __device__ void solve_refine()
-    {
-        solve_prep(3, 0.0);
-        riccati_solve(3);
-        double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
-        ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
-        if (act) expand<XP_REFINE>(3, 0.0, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        if (kind == 3) {
+            for (k = lane; k <= N; k += 32) expand<XP_REFINE>(3, 0.0, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        } else {
+            for (k = lane; k <= N; k += 32) expand<XP_SOLVE>(kind, smu, 0.0, ap, ad, s1, s2, nullptr, dummy);
+        }
         ap = ap_n / ap_d; ad = ad_n / ad_d;
         reduce_step_length(ap, ad, s1, s2);
         __syncwarp();
@@ -773,11 +816,11 @@ struct WppSolver {
     __device__ void lin_residuals(double lnrm[2])
     {
         double ln0 = 0.0, ln1 = 0.0;
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             const double* Hd = k < N ? p.Hd : p.Hde;
             double dv[7], lrg[7];
 #pragma unroll
-            for (int i = 0; i < 7; i++) { dv[i] = S(o.dv + i, k); lrg[i] = S(o.rg + i, k) + Hd[i] * dv[i]; }
+            for (int i = 0; i < 7; i++) { dv[i] = S(o.dv + i, k); lrg[i] = Q<PF_RG>(i) + Hd[i] * dv[i]; }
             double sv[10];
             if (k < N) {
 #pragma unroll
@@ -816,7 +859,7 @@ struct WppSolver {
 
     __device__ void update(double a)
     {
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             double ap = 0, ad = 0, s1 = 0, s2 = 0, dummy = 0;
             expand<XP_UPDATE>(0, 0.0, a, ap, ad, s1, s2, nullptr, dummy);
 #pragma unroll
@@ -833,37 +876,42 @@ struct WppSolver {
     __device__ void run()
     {
         prepare_and_init();
-        residuals();
         alpha = 1.0;
         int kk = 0, n_itref = 0;
         const double inv_nc = 1.0 / nc;
-        for (; kk < p.qp_iter_max && alpha > p.alpha_min &&
-               (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max); kk++) {
+        for (;; kk++) {
+            residuals();
+            if (!(kk < p.qp_iter_max && alpha > p.alpha_min &&
+                  (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max))) break;
             factorize();
-            solve_base(0, 0.0);
-            if (p.pred_corr) {
-                double mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
-                const double tmp = mu_aff / mu;
-                double smu = tmp * tmp * tmp * mu;
-                smu = smu > p.tau_min ? smu : p.tau_min;
-                solve_base(1, smu);
-                if (p.cond_pred_corr) {
-                    const double mu_aff0 = mu_aff;
-                    mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
-                    if (mu_aff > 2.0 * mu_aff0) solve_base(2, smu);
+            // predictor, corrector, (conditional) centering, <= itref_corr_max refinement steps
+            int kind = 0, itref = 0;
+            double smu = 0.0, mu_aff0 = 0.0;
+            for (;;) {
+                solve_any(kind, smu);
+                if (!p.pred_corr) break;
+                if (kind == 0) {
+                    const double mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
+                    const double tmp = mu_aff / mu;
+                    smu = tmp * tmp * tmp * mu;
+                    smu = smu > p.tau_min ? smu : p.tau_min;
+                    mu_aff0 = mu_aff;
+                    kind = 1;
+                    continue;
                 }
-                for (int it = 0; it < p.itref_corr_max; it++) {
-                    double lnrm[2];
-                    lin_residuals(lnrm);
-                    if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
-                    solve_refine();
-                    n_itref++;
+                if (kind == 1 && p.cond_pred_corr) {
+                    const double mu_aff = (sum_lt + alpha * S1 + alpha * alpha * S2) * inv_nc;
+                    if (mu_aff > 2.0 * mu_aff0) { kind = 2; continue; }
                 }
+                if (itref >= p.itref_corr_max) break;
+                double lnrm[2];
+                lin_residuals(lnrm);
+                if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
+                kind = 3; itref++; n_itref++;
             }
             double a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
             update(a);
-            residuals();
         }
         int qs;
         if (kk == p.qp_iter_max) qs = 1;
@@ -871,7 +919,7 @@ struct WppSolver {
         else if (mu != mu || nrm[0] != nrm[0] || nrm[1] != nrm[1] || nrm[2] != nrm[2] || nrm[3] != nrm[3]) qs = 3;
         else qs = 0;
         const int status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate untouched
-        if (act) {
+        for (k = lane; k <= N; k += 32) {
             if (status == 0) {
 #pragma unroll
                 for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += S(o.v + 2 + i, k);
@@ -879,10 +927,10 @@ struct WppSolver {
                     p.U[((size_t)k * 2 + 0) * Bm + b] += S(o.v + 0, k);
                     p.U[((size_t)k * 2 + 1) * Bm + b] += S(o.v + 1, k);
                 }
-    #pragma unroll 1
+#pragma unroll JU
             for (int j = 0; j < M; j++) {
-                    p.SL[((size_t)k * M + j) * Bm + b] += S(o.sl + j, k);
-                    p.SU[((size_t)k * M + j) * Bm + b] += S(o.su + j, k);
+                    p.SL[((size_t)k * M + j) * Bm + b] += Q<PF_SL>(j);
+                    p.SU[((size_t)k * M + j) * Bm + b] += Q<PF_SU>(j);
                 }
             }
             if (k < N) {
@@ -890,8 +938,8 @@ struct WppSolver {
                 for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = S(o.pi + i, k);
             }
             for (int i = 0; i < nct; i++) {
-                p.LAM[((size_t)k * nct + i) * Bm + b] = S(o.lam + i, k);
-                p.T[((size_t)k * nct + i) * Bm + b] = S(o.t + i, k);
+                p.LAM[((size_t)k * nct + i) * Bm + b] = Q<PF_LAM>(i);
+                p.T[((size_t)k * nct + i) * Bm + b] = Q<PF_T>(i);
             }
         }
         if (lane == 0) {
@@ -903,13 +951,18 @@ struct WppSolver {
     }
 };
 
-template <int MT, int NT>
-__global__ void __launch_bounds__(32) b2_rti_solve_wpp(const B2Params p)
+template <int MT, int NT, unsigned SMASK>
+__global__ void __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_SHARED) ? B2_WPP_MINB : 1) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
-    for (int i = blockIdx.x; i < p.B; i += gridDim.x) {
+    double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows
+    for (;;) {
+        int i = 0;
+        if ((threadIdx.x & 31) == 0) i = atomicAdd(p.NEXT, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= p.B) break;
         const int b = p.ORDER ? p.ORDER[i] : i;      // expensive problems first (shorter tail), see b2_order_problems
-        WppSolver<MT, NT> s(p, b, b2_smem);
+        WppSolver<MT, NT, SMASK> s(p, b, b2_smem, gm);
         s.run();
     }
 }

@@ -45,7 +45,9 @@ typedef struct b2mpc_config {
     int32_t integrator;      /* 0 = IRK Gauss-Legendre-4 (reference, :129), 1 = RK4 */
     int32_t qp_iter_max;     /* solver_options.qp_solver_iter_max, :131 */
     int32_t lm_scaled_by_dt; /* acados-version switch for levenberg_marquardt scaling */
-    int32_t kernel;          /* 0 = auto, 1 = thread-per-problem, 2 = warp-per-problem */
+    int32_t kernel;          /* 0 = auto (= 2), 1 = thread-per-problem (cross-check), 2 = warp-per-problem with the node-private
+                                rows in L2-resident global memory (any N <= 128), 3 = warp-per-problem, everything in shared
+                                memory (needs the whole problem to fit: N = 20, M = 5 does) */
     int32_t pred_corr, cond_pred_corr, itref_corr_max, reserved;
     double tf;               /* solver_options.tf, :132 */
     double lm;               /* solver_options.levenberg_marquardt, :128 */
@@ -105,7 +107,7 @@ void b2mpc_default_config(b2mpc_config *cfg, int32_t N, int32_t n_obst, double t
 int b2mpc_create(const b2mpc_config *cfg, b2mpc **out);
 int b2mpc_destroy(b2mpc *h);                                     /* solver teardown */
 int64_t b2mpc_field_len(const b2mpc *h, int field);              /* doubles per problem */
-int64_t b2mpc_workspace_bytes(const b2mpc *h);
+int64_t b2mpc_workspace_bytes(const b2mpc *h);                   /* device scratch of the solve kernel (node-private rows / work arrays) */
 
 /* ocp_solver.set / cost_set / set_params_sparse (:151-152,:164-166,:191-192,:254-258,:305-306) */
 int b2mpc_set(b2mpc *h, int field, const double *dptr, int64_t batch, int layout, void *stream);
@@ -144,7 +146,8 @@ int b2mpc_loop_reset(b2mpc *h, int64_t batch, void *stream);
 int b2mpc_loop_post(b2mpc *h, int64_t batch, const double *dnoise, int32_t random_move,
                     int32_t init_guess_when_error, double tol, void *stream);
 
-/* which solve kernel the handle resolved to: 1 = thread-per-problem (generic), 2 = warp-per-problem */
+/* which solve kernel the handle resolved to: 1 = thread-per-problem, 2 = warp-per-problem (node-private rows in global
+   memory), 3 = warp-per-problem (all shared memory) */
 int b2mpc_kernel(const b2mpc *h);
 /* number of kernels launched by this handle so far (for bench accounting) */
 int64_t b2mpc_launch_count(const b2mpc *h);

@@ -1,0 +1,25 @@
+"""device-timed solves of config 4 (N=100, M=20, tf=5) -- experiment driver"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dynamic-obstacle-avoidance-mpc_b200"))
+import torch
+from b200mpc import BatchedMpcSolver, world
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+N, M, tf = (int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5])) if len(sys.argv) > 5 else (100, 20, 5.0)
+dims = world.MpcDims(N, M, tf)
+sc = world.random_scenarios(B, dims, seed=0)
+solver = BatchedMpcSolver(N, M, tf, max_batch=B, kernel=kern)
+t = {k: torch.from_numpy(sc[k]).cuda() for k in ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")}
+for name in ("x0", "p", "yref", "zl", "Zl"):
+    solver.set(name, t[name])
+ms = []
+for _ in range(4):
+    for name in ("x", "u", "sl", "su"):
+        solver.set(name, t[name])
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); solver.solve(B); e1.record(); torch.cuda.synchronize()
+    ms.append(e0.elapsed_time(e1))
+ms = sorted(ms[1:])
+it = solver.get_int("qp_iter", B).float()
+print(f"N={N} M={M} B={B} kernel={solver.kernel_name} ms={ms[len(ms)//2]:.3f} solves/s={B/ms[len(ms)//2]*1e3:.0f} qp_iter_mean={it.mean().item():.3f} ws={solver.workspace_bytes/1e6:.0f}MB")
