@@ -37,11 +37,11 @@ __constant__ unsigned char B2_BATAB[5][7] = {
 };
 
 // node-private fields (see header): rows per field are nct for the first four, M for the obstacle fields
-enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD,                     // per constraint; dd doubles as dlam
+enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; dd = dlam (or dt*dlam of the predictor), dt = dt
        PF_B, PF_G, PF_RG, PF_XU,                            // 5, 7, 7, 6 rows
        PF_CX, PF_CY, PF_LG, PF_UG, PF_ZLQ, PF_ZZLQ, PF_SLI, PF_SUI, PF_SL, PF_SU,
        PF_LRGSL, PF_LRGSU, PF_DSL, PF_DSU, PF_DLI, PF_DUI, PF_COUNT };
-#define B2_WPP_ALL_SHARED 0xffffffu
+#define B2_WPP_ALL_SHARED 0x1ffffffu
 // Placement used by default: EVERY node-private field in global memory.  Measured on B200 (N=20, M=5, 4096 problems,
 // profiles/experiments/r01_hybrid_layout.md): all global, 12 CTAs/SM 11.6 ms; lam,t shared, 7 CTAs/SM 13.1 ms;
 // lam,t,1/t,dlam shared, 5 CTAs/SM 14.3 ms; all shared, 4 CTAs/SM 12.7 ms.
@@ -57,7 +57,7 @@ struct WOff {
     int gtotal;                                                                 // global-memory rows
     __host__ __device__ static int pf_rows(int f, int M)
     {
-        return f <= PF_DD ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
+        return f <= PF_DT ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
     }
     __host__ __device__ WOff(int M, unsigned smask)
     {
@@ -87,11 +87,27 @@ __host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned sma
     return (size_t)WOff(M, smask).gtotal * b2_wpp_gstride(N);
 }
 
-__device__ __forceinline__ double b2_warp_max(double v)
+// y ~ 1/x (a few ulp) -> one Newton step: the result is within an ulp of the correctly rounded reciprocal
+__device__ __forceinline__ double b2_rcp_polish(double x, double y) { return fma(y, fma(-x, y, 1.0), y); }
+
+// Warp-wide maximum of NON-NEGATIVE doubles (norms; a NaN wins): the IEEE bit pattern of such values is monotone as an
+// unsigned integer, so two REDUX.MAX.U32 (high word, then low word among the lanes holding the maximal high word)
+// replace five rounds of double shuffles + compares.  Exact.
+__device__ __forceinline__ double b2_warp_max_nonneg(double v)
 {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
-    return v;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+// Warp-wide maximum of NEGATIVE doubles (the step-length ratios in negative-reciprocal form): largest value = smallest
+// magnitude = smallest bit pattern.
+__device__ __forceinline__ double b2_warp_max_neg(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
 }
 __device__ __forceinline__ double b2_warp_sum(double v)
 {
@@ -191,7 +207,11 @@ struct WppSolver {
 #pragma unroll
                 for (int i = 0; i < 5; i++) v[2 + i] = p.X0[(size_t)i * Bm + b] - xk[i];
             }
-            for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; }
+            for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; Q<PF_DT>(i) = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.dv + i, k) = 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; i++) S(o.dpi + i, k) = 0.0;
 #pragma unroll
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
@@ -225,7 +245,7 @@ struct WppSolver {
                 Q<PF_LAM>(o_lg + j) = p.mu0 / tl; Q<PF_LAM>(o_ug + j) = p.mu0 / tu;
                 Q<PF_T>(o_ls + j) = 1.0; Q<PF_T>(o_us + j) = 1.0;
                 Q<PF_LAM>(o_ls + j) = p.mu0; Q<PF_LAM>(o_us + j) = p.mu0;
-                Q<PF_SL>(j) = 0.0; Q<PF_SU>(j) = 0.0;
+                Q<PF_SL>(j) = 0.0; Q<PF_SU>(j) = 0.0; Q<PF_DSL>(j) = 0.0; Q<PF_DSU>(j) = 0.0;
             }
 #pragma unroll
             for (int i = 0; i < 7; i++) S(o.v + i, k) = v[i];
@@ -239,16 +259,32 @@ struct WppSolver {
     __device__ __forceinline__ double g_box_l(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return v[b2_slot2v(s)] - lb; }
     __device__ __forceinline__ double g_box_u(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return ub - v[b2_slot2v(s)]; }
 
-    // ---- KKT residuals ---------------------------------------------------------------------------
-    __device__ void residuals()
+    // ---- head of an interior-point iteration: ONE pass over the node-private rows ---------------------
+    //  (1) apply the previous step with length a (a = 0 on entry: the step rows are zeroed by prepare_and_init),
+    //  (2) KKT residuals, their norms and mu at the new iterate,
+    //  (3) barrier/slack elimination: 1/t, D^-1, condensed node Hessian (-> rows cv[0..6], cpi[0] for the recursion),
+    //  (4) condensed gradient of the AFFINE right-hand side (-> rows hg[0..6], what solve_prep(0) would produce).
+    // Fused because every one of these walks the same multipliers/slacks: with the private rows in L2 a pass costs a
+    // round trip per obstacle, and each pass is straight-line code that has to be fetched.  (3)+(4) are wasted on the
+    // last (converged) iteration only.
+    __device__ void head(double a)
     {
+        for (k = lane; k <= N; k += 32) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) S(o.v + i, k) += a * S(o.dv + i, k);
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) S(o.pi + i, k) += a * S(o.dpi + i, k);
+            }
+        }
+        __syncwarp();
         double sum = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
         for (k = lane; k <= N; k += 32) {
-            double v[7], rg[7];
+            double v[7], rg[7], Hx[7], gt[7], hxy = 0.0;
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
 #pragma unroll
-            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); }
+            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
             double sv[10];
             if (k < N) {
 #pragma unroll
@@ -268,37 +304,83 @@ struct WppSolver {
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
                 const int iv = b2_slot2v(s);
-                const double ll = Q<PF_LAM>(o_lb + s), lu_ = Q<PF_LAM>(o_ub + s);
-                const double tl = Q<PF_T>(o_lb + s), tu = Q<PF_T>(o_ub + s);
+                const int il = o_lb + s, iu = o_ub + s;
+                double ll = Q<PF_LAM>(il) + a * Q<PF_DD>(il), lu_ = Q<PF_LAM>(iu) + a * Q<PF_DD>(iu);
+                double tl = Q<PF_T>(il) + a * Q<PF_DT>(il), tu = Q<PF_T>(iu) + a * Q<PF_DT>(iu);
+                if (ll <= p.lam_min) ll = p.lam_min;
+                if (lu_ <= p.lam_min) lu_ = p.lam_min;
+                if (tl <= p.t_min) tl = p.t_min;
+                if (tu <= p.t_min) tu = p.t_min;
+                Q<PF_LAM>(il) = ll; Q<PF_LAM>(iu) = lu_; Q<PF_T>(il) = tl; Q<PF_T>(iu) = tu;
                 rg[iv] += -ll + lu_;
                 const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
                 n2 = fmax(n2, fmax(fabs(rdl), fabs(rdu)));
                 const double ml = ll * tl, mu_ = lu_ * tu;
                 n3 = fmax(n3, fmax(fabs(ml), fabs(mu_)));
                 sum += ml; sum += mu_;
+                const double rlu = 1.0 / (tl * tu);                    // one division per pair: 1/tl = tu/(tl tu)
+                const double til = b2_rcp_polish(tl, rlu * tu), tiu = b2_rcp_polish(tu, rlu * tl);
+                Q<PF_TINV>(il) = til; Q<PF_TINV>(iu) = tiu;
+                Hx[iv] += ll * til + lu_ * tiu;
+                gt[iv] += (ml + ll * rdl) * til - (mu_ + lu_ * rdu) * tiu;
             }
             const double Zuq = sc * p.Zu;
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
+                const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
+                double l0 = Q<PF_LAM>(i0) + a * Q<PF_DD>(i0), l1 = Q<PF_LAM>(i1) + a * Q<PF_DD>(i1);
+                double l2 = Q<PF_LAM>(i2) + a * Q<PF_DD>(i2), l3 = Q<PF_LAM>(i3) + a * Q<PF_DD>(i3);
+                double t0 = Q<PF_T>(i0) + a * Q<PF_DT>(i0), t1 = Q<PF_T>(i1) + a * Q<PF_DT>(i1);
+                double t2 = Q<PF_T>(i2) + a * Q<PF_DT>(i2), t3 = Q<PF_T>(i3) + a * Q<PF_DT>(i3);
+                if (l0 <= p.lam_min) l0 = p.lam_min;
+                if (l1 <= p.lam_min) l1 = p.lam_min;
+                if (l2 <= p.lam_min) l2 = p.lam_min;
+                if (l3 <= p.lam_min) l3 = p.lam_min;
+                if (t0 <= p.t_min) t0 = p.t_min;
+                if (t1 <= p.t_min) t1 = p.t_min;
+                if (t2 <= p.t_min) t2 = p.t_min;
+                if (t3 <= p.t_min) t3 = p.t_min;
+                Q<PF_LAM>(i0) = l0; Q<PF_LAM>(i1) = l1; Q<PF_LAM>(i2) = l2; Q<PF_LAM>(i3) = l3;
+                Q<PF_T>(i0) = t0; Q<PF_T>(i1) = t1; Q<PF_T>(i2) = t2; Q<PF_T>(i3) = t3;
+                const double s_l = Q<PF_SL>(j) + a * Q<PF_DSL>(j), s_u = Q<PF_SU>(j) + a * Q<PF_DSU>(j);
+                Q<PF_SL>(j) = s_l; Q<PF_SU>(j) = s_u;
                 const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
                 const double cv = cx * v[2] + cy * v[3];
-                const double llg = Q<PF_LAM>(o_lg + j), lug = Q<PF_LAM>(o_ug + j), lls = Q<PF_LAM>(o_ls + j), lus = Q<PF_LAM>(o_us + j);
-                const double tlg = Q<PF_T>(o_lg + j), tug = Q<PF_T>(o_ug + j), tls = Q<PF_T>(o_ls + j), tus = Q<PF_T>(o_us + j);
-                const double dl = lug - llg;
+                const double dl = l1 - l0;
                 rg[2] += cx * dl; rg[3] += cy * dl;
-                const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
                 const double sli = Q<PF_SLI>(j), sui = Q<PF_SUI>(j);
-                const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - llg - lls;
-                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * sui) - lug - lus;
+                const double Zlq = Q<PF_ZZLQ>(j);
+                const double rgsl = Zlq * s_l + Q<PF_ZLQ>(j) - l0 - l2;
+                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * sui) - l1 - l3;
                 n0 = fmax(n0, fmax(fabs(rgsl), fabs(rgsu)));
-                const double rdlg = cv + s_l - Q<PF_LG>(j) - tlg;
-                const double rdug = Q<PF_UG>(j) - cv + s_u - tug;
-                const double rdls = s_l + sli - tls;
-                const double rdus = s_u + sui - tus;
-                n2 = fmax(n2, fmax(fmax(fabs(rdlg), fabs(rdug)), fmax(fabs(rdls), fabs(rdus))));
-                const double m0 = llg * tlg, m1 = lug * tug, m2 = lls * tls, m3 = lus * tus;
+                const double rd0 = cv + s_l - Q<PF_LG>(j) - t0;
+                const double rd1 = Q<PF_UG>(j) - cv + s_u - t1;
+                const double rd2 = s_l + sli - t2;
+                const double rd3 = s_u + sui - t3;
+                n2 = fmax(n2, fmax(fmax(fabs(rd0), fabs(rd1)), fmax(fabs(rd2), fabs(rd3))));
+                const double m0 = l0 * t0, m1 = l1 * t1, m2 = l2 * t2, m3 = l3 * t3;
                 n3 = fmax(n3, fmax(fmax(fabs(m0), fabs(m1)), fmax(fabs(m2), fabs(m3))));
                 sum += m0; sum += m1; sum += m2; sum += m3;
+                // one division for the four slacks of the obstacle (t in [1e-16, ~1e5]: the product stays in range)
+                const double p01 = t0 * t1, p23 = t2 * t3;
+                const double r4 = 1.0 / (p01 * p23);
+                const double r01 = r4 * p23, r23 = r4 * p01;
+                const double ti0 = b2_rcp_polish(t0, r01 * t1), ti1 = b2_rcp_polish(t1, r01 * t0);
+                const double ti2 = b2_rcp_polish(t2, r23 * t3), ti3 = b2_rcp_polish(t3, r23 * t2);
+                Q<PF_TINV>(i0) = ti0; Q<PF_TINV>(i1) = ti1; Q<PF_TINV>(i2) = ti2; Q<PF_TINV>(i3) = ti3;
+                const double Gl = l0 * ti0, Gu = l1 * ti1, Gls = l2 * ti2, Gus = l3 * ti3;
+                const double dl_ = Zlq + Gl + Gls, du_ = Zuq + Gu + Gus;
+                const double rd_ = 1.0 / (dl_ * du_);
+                const double Dli = b2_rcp_polish(dl_, rd_ * du_), Dui = b2_rcp_polish(du_, rd_ * dl_);
+                Q<PF_DLI>(j) = Dli; Q<PF_DUI>(j) = Dui;
+                const double weff = Gl * (Zlq + Gls) * Dli + Gu * (Zuq + Gus) * Dui;
+                Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
+                // affine right-hand side (kind 0: rm = lam t)
+                const double q0 = (m0 + l0 * rd0) * ti0, q1 = (m1 + l1 * rd1) * ti1;
+                const double q2 = (m2 + l2 * rd2) * ti2, q3 = (m3 + l3 * rd3) * ti3;
+                const double rhol = rgsl + q0 + q2, rhou = rgsu + q1 + q3;
+                const double coef = (q0 - Gl * rhol * Dli) - (q1 - Gu * rhou * Dui);
+                gt[2] += cx * coef; gt[3] += cy * coef;
             }
             if (k < N) {
                 double rb[5];
@@ -313,52 +395,18 @@ struct WppSolver {
             if (k == 0) { rg[2] = rg[3] = rg[4] = rg[5] = rg[6] = 0.0; }
             if (k == N) { rg[0] = rg[1] = 0.0; }
 #pragma unroll
-            for (int i = 0; i < 7; i++) { Q<PF_RG>(i) = rg[i]; n0 = fmax(n0, fabs(rg[i])); }
+            for (int i = 0; i < 7; i++) {
+                Q<PF_RG>(i) = rg[i]; n0 = fmax(n0, fabs(rg[i]));
+                S(o.hg + i, k) = rg[i] + gt[i];
+                S(o.cv + i, k) = Hx[i];
+            }
+            S(o.cpi + 0, k) = hxy;
         }
         sum = b2_warp_sum(sum);
-        nrm[0] = b2_warp_max(n0); nrm[1] = b2_warp_max(n1); nrm[2] = b2_warp_max(n2); nrm[3] = b2_warp_max(n3);
+        nrm[0] = b2_warp_max_nonneg(n0); nrm[1] = b2_warp_max_nonneg(n1); nrm[2] = b2_warp_max_nonneg(n2); nrm[3] = b2_warp_max_nonneg(n3);
         sum_lt = sum;
         mu = sum / nc;
         __syncwarp();
-    }
-
-    // ---- barrier/slack elimination -> condensed node Hessians (lane k), then the Riccati recursion ---
-    __device__ void factorize()
-    {
-        for (k = lane; k <= N; k += 32) {
-            const double* Hd = k < N ? p.Hd : p.Hde;
-            const double sc = scal(k);
-            double Hx[7], hxy = 0.0;
-#pragma unroll
-            for (int i = 0; i < 7; i++) Hx[i] = Hd[i] + p.reg_prim;
-#pragma unroll
-            for (int s = 0; s < 6; s++) {
-                if (!box_on(s, k)) continue;
-                const double til = 1.0 / Q<PF_T>(o_lb + s), tiu = 1.0 / Q<PF_T>(o_ub + s);
-                Q<PF_TINV>(o_lb + s) = til; Q<PF_TINV>(o_ub + s) = tiu;
-                Hx[b2_slot2v(s)] += Q<PF_LAM>(o_lb + s) * til + Q<PF_LAM>(o_ub + s) * tiu;
-            }
-            const double Zuq = sc * p.Zu;
-#pragma unroll JU
-            for (int j = 0; j < M; j++) {
-                const double t0 = 1.0 / Q<PF_T>(o_lg + j), t1 = 1.0 / Q<PF_T>(o_ug + j);
-                const double t2 = 1.0 / Q<PF_T>(o_ls + j), t3 = 1.0 / Q<PF_T>(o_us + j);
-                Q<PF_TINV>(o_lg + j) = t0; Q<PF_TINV>(o_ug + j) = t1; Q<PF_TINV>(o_ls + j) = t2; Q<PF_TINV>(o_us + j) = t3;
-                const double Gl = Q<PF_LAM>(o_lg + j) * t0, Gu = Q<PF_LAM>(o_ug + j) * t1;
-                const double Gls = Q<PF_LAM>(o_ls + j) * t2, Gus = Q<PF_LAM>(o_us + j) * t3;
-                const double Zlq = Q<PF_ZZLQ>(j);
-                const double Dli = 1.0 / (Zlq + Gl + Gls), Dui = 1.0 / (Zuq + Gu + Gus);
-                Q<PF_DLI>(j) = Dli; Q<PF_DUI>(j) = Dui;
-                const double weff = Gl * (Zlq + Gls) * Dli + Gu * (Zuq + Gus) * Dui;
-                const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
-                Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
-            }
-#pragma unroll
-            for (int i = 0; i < 7; i++) S(o.hg + i, k) = Hx[i];
-            S(o.hg + 7, k) = hxy;
-        }
-        __syncwarp();
-        riccati_factorize();
     }
 
     // Backward Riccati recursion in SQUARE-ROOT form (what HPIPM does with square_root_alg = 1):
@@ -385,8 +433,8 @@ struct WppSolver {
         double* const scr = sm + o.total * NS;
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
-            if (mi == mj) m = S(o.hg + mi, kk);
-            if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
+            if (mi == mj) m = S(o.cv + mi, kk);                 // condensed node Hessian, left there by head()
+            if (mi == 3 && mj == 2) m = S(o.cpi + 0, kk);
             if (kk < N) {
                 // A: AL = [B A]^T Lxx(kk+1)
                 {
@@ -685,10 +733,12 @@ struct WppSolver {
                 dlu = -(rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * dtu) * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = keep_dd ? dtl * dll : dll;
                 Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
+                Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
             } else if (MODE == XP_REFINE) {
                 dll = Q<PF_DD>(il) - ll * cv[iv] * Q<PF_TINV>(il);
                 dlu = Q<PF_DD>(iu) + lu_ * cv[iv] * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
+                Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
             } else {
                 dll = Q<PF_DD>(il); dlu = Q<PF_DD>(iu);
             }
@@ -741,11 +791,11 @@ struct WppSolver {
                 dl0 = Q<PF_DD>(i0); dl1 = Q<PF_DD>(i1); dl2 = Q<PF_DD>(i2); dl3 = Q<PF_DD>(i3);
             }
             const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
+            if (MODE == XP_SOLVE || MODE == XP_REFINE) { Q<PF_DT>(i0) = dt0; Q<PF_DT>(i1) = dt1; Q<PF_DT>(i2) = dt2; Q<PF_DT>(i3) = dt3; }
             consume<MODE>(i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
             consume<MODE>(i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
             consume<MODE>(i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
             consume<MODE>(i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
-            if (MODE == XP_UPDATE) { Q<PF_SL>(j) = s_l + a * dsl; Q<PF_SU>(j) = s_u + a * dsu; }
             if (MODE == XP_LIN) {
                 const double dl = dl1 - dl0;
                 lrg[2] += cx * dl; lrg[3] += cy * dl;
@@ -773,18 +823,13 @@ struct WppSolver {
             if (ap_n * dti < t * ap_d) { ap_n = t; ap_d = dti; }
             s1 += l * dti + t * dli;
             s2 += dli * dti;
-        } else if (MODE == XP_UPDATE) {
-            double ln = l + a * dli, tn = t + a * dti;
-            if (ln <= p.lam_min) ln = p.lam_min;
-            if (tn <= p.t_min) tn = p.t_min;
-            Q<PF_LAM>(i) = ln; Q<PF_T>(i) = tn;
         }
     }
 
     __device__ void reduce_step_length(double ap, double ad, double s1, double s2)
     {
         // max of the negative reciprocals == min of the admissible step lengths
-        ap = b2_warp_max(ap); ad = b2_warp_max(ad);
+        ap = b2_warp_max_neg(ap); ad = b2_warp_max_neg(ad);
         S1 = b2_warp_sum(s1); S2 = b2_warp_sum(s2);
         alpha = -(ap > ad ? ap : ad);
     }
@@ -798,7 +843,7 @@ struct WppSolver {
     {
         rm_cdd = kind == 1 ? 1.0 : 0.0;
         rm_smu = kind == 0 ? 0.0 : smu;
-        solve_prep(kind, smu);
+        if (kind != 0) solve_prep(kind, smu);          // the affine right-hand side was assembled by head()
         riccati_solve(kind);
         double ap = -1.0, ad = -1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
         ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
@@ -853,22 +898,7 @@ struct WppSolver {
 #pragma unroll
             for (int i = 0; i < 7; i++) { S(o.hg + i, k) = lrg[i]; ln0 = fmax(ln0, fabs(lrg[i])); }
         }
-        lnrm[0] = b2_warp_max(ln0); lnrm[1] = b2_warp_max(ln1);
-        __syncwarp();
-    }
-
-    __device__ void update(double a)
-    {
-        for (k = lane; k <= N; k += 32) {
-            double ap = 0, ad = 0, s1 = 0, s2 = 0, dummy = 0;
-            expand<XP_UPDATE>(0, 0.0, a, ap, ad, s1, s2, nullptr, dummy);
-#pragma unroll
-            for (int i = 0; i < 7; i++) S(o.v + i, k) += a * S(o.dv + i, k);
-            if (k < N) {
-#pragma unroll
-                for (int i = 0; i < 5; i++) S(o.pi + i, k) += a * S(o.dpi + i, k);
-            }
-        }
+        lnrm[0] = b2_warp_max_nonneg(ln0); lnrm[1] = b2_warp_max_nonneg(ln1);
         __syncwarp();
     }
 
@@ -879,11 +909,12 @@ struct WppSolver {
         alpha = 1.0;
         int kk = 0, n_itref = 0;
         const double inv_nc = 1.0 / nc;
+        double a = 0.0;
         for (;; kk++) {
-            residuals();
+            head(a);
             if (!(kk < p.qp_iter_max && alpha > p.alpha_min &&
                   (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max))) break;
-            factorize();
+            riccati_factorize();
             // predictor, corrector, (conditional) centering, <= itref_corr_max refinement steps
             int kind = 0, itref = 0;
             double smu = 0.0, mu_aff0 = 0.0;
@@ -909,9 +940,8 @@ struct WppSolver {
                 if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
                 kind = 3; itref++; n_itref++;
             }
-            double a = alpha;
+            a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-            update(a);
         }
         int qs;
         if (kk == p.qp_iter_max) qs = 1;
