@@ -31,6 +31,8 @@ static int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(B2MPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+#define B2_ORDER_MAXKEYS 72         // >= number of keys of the launch-order counting sort (B2_ORDER_NKEYS)
+
 struct b2mpc {
     b2mpc_config cfg;
     int N, M, Bm, nct;
@@ -192,7 +194,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     if (h->kernel != 1) {
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
         if (h->wpp_smem > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
-        if (cudaMalloc(&h->order, sizeof(int32_t) * ((size_t)h->Bm + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
+        if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 2 * B2_ORDER_MAXKEYS + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
         cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
@@ -627,25 +629,44 @@ extern "C" int b2mpc_loop_post(b2mpc* h, int64_t batch, const double* dnoise, in
     return B2MPC_OK;
 }
 
-// Launch-order heuristic for the warp kernel.  Interior-point iteration counts range from 13 to the limit;
-// problems whose linearisation point lies inside an obstacle's safety disc (negative h somewhere on the
-// horizon) are the slow ones (mu0 = 1 against multipliers ~1e5).  CTAs are dispatched in index order, so
-// putting those first shortens the tail of the launch.  Pure scheduling: per-problem results are unaffected.
-__global__ void b2_order_problems(const double* __restrict__ X, const double* __restrict__ P, int32_t* __restrict__ order,
-                                  int32_t* __restrict__ cnt, int N, int M, double r2, int B, int Bm)
+// Launch-order heuristic for the warp kernel.  Interior-point iteration counts range from 13 to the limit (50);
+// the persistent CTAs pull problems from a queue, so the order of the queue decides the tail of the launch.
+// Predictor (4096 random scenarios, profiles/experiments/r01_launch_order.md): the FIRST shooting node whose
+// linearisation point lies inside an obstacle's safety disc -- node 0/1: 45 iterations on average (62 % hit the limit),
+// node 10: 30, node 20: 15; none: 15-20 depending on the smallest clearance.  Spearman correlation with the iteration
+// count 0.84.  Counting sort by that key, expensive first.  Pure scheduling: per-problem results are unaffected.
+#define B2_ORDER_NODEKEYS 64
+#define B2_ORDER_NKEYS (B2_ORDER_NODEKEYS + 3)
+__global__ void b2_order_keys(const double* __restrict__ X, const double* __restrict__ P, int32_t* __restrict__ key,
+                              int32_t* __restrict__ hist, int N, int M, double r2, int B, int Bm)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    bool inside = false;
-    for (int k = 0; k <= N && !inside; k += 4) {
+    int first = -1;
+    double hmin = 1e300;
+    for (int k = 0; k <= N && first < 0; k++) {
         const double x = X[((size_t)k * 5 + 0) * Bm + b], y = X[((size_t)k * 5 + 1) * Bm + b];
         for (int j = 0; j < M; j++) {
             const double dx = x - P[((size_t)k * 2 * M + 2 * j) * Bm + b], dy = y - P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b];
-            inside |= (dx * dx + dy * dy < r2);
+            const double h = dx * dx + dy * dy - r2;
+            hmin = h < hmin ? h : hmin;
+            if (h < 0.0) first = k;
         }
     }
-    if (inside) order[atomicAdd(&cnt[0], 1)] = b;
-    else order[B - 1 - atomicAdd(&cnt[1], 1)] = b;
+    const int kk = first >= 0 ? (first < B2_ORDER_NODEKEYS ? first : B2_ORDER_NODEKEYS - 1)
+                              : B2_ORDER_NODEKEYS + (hmin < 1.0 ? 0 : (hmin < 3.0 ? 1 : 2));
+    key[b] = kk;
+    atomicAdd(&hist[kk], 1);
+}
+__global__ void b2_order_scatter(const int32_t* __restrict__ key, const int32_t* __restrict__ hist, int32_t* __restrict__ fill,
+                                 int32_t* __restrict__ order, int nkeys, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int kk = key[b];
+    int start = 0;
+    for (int c = 0; c < kk; c++) start += hist[c];
+    order[start + atomicAdd(&fill[kk], 1)] = b;
 }
 
 // ------------------------------------------------------------------ the solve
@@ -657,13 +678,18 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     B2Params p = h->prm;
     p.B = (int)batch;
     if (h->kernel != 1) {
-        int32_t* cnt = h->order + h->Bm;                 // [inside count, outside count, work counter]
-        CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * sizeof(int32_t), st));
-        b2_order_problems<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], h->order, cnt, h->N, h->M,
-                                                                         h->cfg.r2, (int)batch, h->Bm);
-        h->launches++;
+        // order buffer: [order (Bm) | key (Bm) | hist (MAXKEYS) | fill (MAXKEYS) | work counter]
+        int32_t* key = h->order + h->Bm;
+        int32_t* hist = key + h->Bm;
+        int32_t* fill = hist + B2_ORDER_MAXKEYS;
+        int32_t* next = fill + B2_ORDER_MAXKEYS;
+        CUDA_TRY(cudaMemsetAsync(hist, 0, (2 * B2_ORDER_MAXKEYS + 4) * sizeof(int32_t), st));
+        const unsigned ob = (unsigned)((batch + 127) / 128);
+        b2_order_keys<<<ob, 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], key, hist, h->N, h->M, h->cfg.r2, (int)batch, h->Bm);
+        b2_order_scatter<<<ob, 128, 0, st>>>(key, hist, fill, h->order, B2_ORDER_NKEYS, (int)batch);
+        h->launches += 2;
         p.ORDER = h->order;
-        p.NEXT = cnt + 2;
+        p.NEXT = next;
         if (h->wpp_fn_small && batch <= h->small_batch_max) {
             h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
         } else {

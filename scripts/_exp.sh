@@ -1,4 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-python scripts/time_solve.py 4096 2 7
-python scripts/time_solve.py 32768 2 5
-python scripts/dump_parity.py 2>&1 | grep "kernel 2"
+for i in 1 2; do
+python scripts/time_solve.py 4096 2 11
+B2MPC_EXPERIMENT_ORDER_MODE=1 python scripts/time_solve.py 4096 2 11
+done
+python scripts/time_solve.py 4096 2 11 7
+B2MPC_EXPERIMENT_ORDER_MODE=1 python scripts/time_solve.py 4096 2 11 7
