@@ -76,7 +76,7 @@ struct WOff {
 };
 
 __host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd shared-memory row stride
-__host__ __device__ inline int b2_wpp_gstride(int N) { return (N + 1 + 3) & ~3; }    // global row stride: 32 B sectors
+__host__ __device__ inline int b2_wpp_gstride(int N) { return N + 1; }               // global rows packed (footprint over sector alignment)
 #define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
 __host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned smask)
 {
