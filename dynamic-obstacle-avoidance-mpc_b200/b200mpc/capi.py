@@ -10,12 +10,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200mpc.so")
 
 # field ids (include/b200mpc.h)
-X0, P, YREF, ZL, ZZL, X, U, SL, SU, PI, LAM, T, STATS, GOAL, OBST, MARGIN, U0 = range(17)
-STATUS, QP_ITER, QP_STATUS, STEPS, DONE, OOB, NFAIL = range(7)
+X0, P, YREF, ZL, ZZL, X, U, SL, SU, PI, LAM, T, STATS, GOAL, OBST, MARGIN, U0, NLP_RES = range(18)
+STATUS, QP_ITER, QP_STATUS, STEPS, DONE, OOB, NFAIL, SQP_ITER = range(8)
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 FIELD_NAMES = {"x0": X0, "p": P, "yref": YREF, "zl": ZL, "Zl": ZZL, "x": X, "u": U, "sl": SL, "su": SU,
-               "pi": PI, "lam": LAM, "t": T, "stats": STATS, "goal": GOAL, "obst": OBST, "margin": MARGIN, "u0": U0}
-IFIELD_NAMES = {"status": STATUS, "qp_iter": QP_ITER, "qp_status": QP_STATUS, "steps": STEPS, "done": DONE, "oob": OOB, "nfail": NFAIL}
+               "pi": PI, "lam": LAM, "t": T, "stats": STATS, "goal": GOAL, "obst": OBST, "margin": MARGIN, "u0": U0,
+               "nlp_res": NLP_RES}
+IFIELD_NAMES = {"status": STATUS, "qp_iter": QP_ITER, "qp_status": QP_STATUS, "steps": STEPS, "done": DONE, "oob": OOB, "nfail": NFAIL,
+                "sqp_iter": SQP_ITER}
 
 
 class Config(C.Structure):
@@ -30,6 +32,7 @@ class Config(C.Structure):
         ("mu0", C.c_double), ("alpha_min", C.c_double), ("res_g_max", C.c_double), ("res_b_max", C.c_double),
         ("res_d_max", C.c_double), ("res_m_max", C.c_double),
         ("reg_prim", C.c_double), ("lam_min", C.c_double), ("t_min", C.c_double), ("tau_min", C.c_double), ("thr0", C.c_double),
+        ("nlp_solver", C.c_int32), ("nlp_iter_max", C.c_int32), ("nlp_tol", C.c_double * 4),
     ]
 
 
@@ -45,7 +48,7 @@ EXPORTS = [
     "b2mpc_set_host", "b2mpc_get_host", "b2mpc_get_i32_host", "b2mpc_field_ptr",
     "b2mpc_prepare_slack", "b2mpc_reset", "b2mpc_solve", "b2mpc_sim", "b2mpc_shift",
     "b2mpc_launch_count", "b2mpc_kernel", "b2mpc_solve_host", "b2mpc_dfma_peak",
-    "b2mpc_obst_predict", "b2mpc_loop_reset", "b2mpc_loop_post",
+    "b2mpc_obst_predict", "b2mpc_loop_reset", "b2mpc_loop_post", "b2mpc_solve_sqp",
 ]
 
 
@@ -78,6 +81,7 @@ def lib():
     L.b2mpc_reset.argtypes = [vp, vp, i64, vp]
     for name in ("b2mpc_prepare_slack", "b2mpc_solve", "b2mpc_sim", "b2mpc_shift"):
         getattr(L, name).argtypes = [vp, i64, vp]
+    L.b2mpc_solve_sqp.argtypes = [vp, i64, i32, dp, vp]
     L.b2mpc_solve_host.argtypes = [vp, i64] + [vp] * 11 + [vp]
     L.b2mpc_dfma_peak.argtypes = [C.c_int, dp]
     L.b2mpc_obst_predict.argtypes = [vp, i64, i32, vp]
@@ -88,7 +92,7 @@ def lib():
         if name not in ("b2mpc_last_error", "b2mpc_default_config", "b2mpc_field_len", "b2mpc_workspace_bytes",
                         "b2mpc_launch_count", "b2mpc_field_ptr"):
             fn.restype = C.c_int
-    if L.b2mpc_abi_version() != 1:
+    if L.b2mpc_abi_version() != 2:
         raise B2mpcError("libb200mpc ABI version mismatch")
     _lib = L
     return L

@@ -33,7 +33,7 @@ class BatchedMpcSolver:
             capi.ZZL: (N + 1, n_obst), capi.X: (N + 1, 5), capi.U: (N, 2), capi.SL: (N + 1, n_obst),
             capi.SU: (N + 1, n_obst), capi.PI: (N, 5), capi.LAM: (N + 1, 12 + 4 * n_obst),
             capi.T: (N + 1, 12 + 4 * n_obst), capi.STATS: (8,), capi.GOAL: (2,), capi.OBST: (n_obst, 4),
-            capi.MARGIN: (2,), capi.U0: (2,),
+            capi.MARGIN: (2,), capi.U0: (2,), capi.NLP_RES: (4,),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -111,6 +111,24 @@ class BatchedMpcSolver:
     def solve(self, batch):
         """ocp_solver.solve(), :195 -- asynchronous on the current stream."""
         capi.check(capi.lib().b2mpc_solve(self._h, batch, self._stream()))
+
+    def solve_sqp(self, batch, max_iter=0, tol=None):
+        """acados' full `SQP` (nlp_solver_type 'SQP': residual test -> QP -> full step, repeated) for every problem in
+        ONE launch; max_iter = nlp_solver_max_iter, tol = (tol_stat, tol_eq, tol_ineq, tol_comp); 0 / None take the
+        handle's configuration.  Status 0 converged, 2 max_iter, 4 QP failure; 'sqp_iter', 'nlp_res' hold the
+        statistics, 'qp_iter' the interior-point iterations in total.  The reference itself runs SQP_RTI (:130)."""
+        tp = None
+        if tol is not None:
+            tp = (C.c_double * 4)(*[float(v) for v in tol])
+        capi.check(capi.lib().b2mpc_solve_sqp(self._h, batch, int(max_iter), tp, self._stream()))
+
+    def reset_multipliers(self, batch):
+        """Forget pi / lam / t (what ocp_solver.reset() does to the multipliers) without touching the iterate: the
+        full-SQP mode's first convergence test reads them."""
+        z = self.torch.zeros
+        dev = f"cuda:{self.device}"
+        for f in (capi.PI, capi.LAM, capi.T):
+            self.set(f, z((batch,) + self._shapes[f], dtype=self.torch.float64, device=dev))
 
     def sim(self, batch):
         """ocp_integrator.solve(), :207-212."""

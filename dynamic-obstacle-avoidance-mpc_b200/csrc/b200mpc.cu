@@ -54,6 +54,7 @@ struct b2mpc {
     double* wpriv;                   // node-private rows of the resident CTAs
     size_t wpriv_bytes;
     void (*wpp_fn_small)(const B2Params);   // auto mode: all-shared instantiation for batches that fit the GPU at once
+    void (*wpp_fn_sqp)(const B2Params);     // full-SQP instantiation (same layout, grid and shared memory as wpp_fn)
     size_t wpp_smem_small;
     int small_batch_max;
     B2Params prm;
@@ -81,6 +82,9 @@ extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst,
     c->mu0 = 1e0; c->alpha_min = 1e-8;                             // acados' HPIPM defaults
     c->res_g_max = 1e-6; c->res_b_max = 1e-8; c->res_d_max = 1e-8; c->res_m_max = 1e-8;
     c->reg_prim = 1e-15; c->lam_min = 1e-16; c->t_min = 1e-16; c->tau_min = 1e-16; c->thr0 = 1e-1;
+    c->nlp_solver = 0;                                             // 'SQP_RTI', robot_ocp_problem.py:130
+    c->nlp_iter_max = 100;                                         // acados defaults for the full-SQP mode
+    for (int i = 0; i < 4; i++) c->nlp_tol[i] = 1e-6;
 }
 
 static void fill_params(b2mpc* h)
@@ -92,6 +96,8 @@ static void fill_params(b2mpc* h)
     p.integrator = c.integrator; p.qp_iter_max = c.qp_iter_max;
     p.pred_corr = c.pred_corr; p.cond_pred_corr = c.cond_pred_corr; p.itref_corr_max = c.itref_corr_max;
     p.nct = h->nct;
+    p.nlp_iter_max = c.nlp_iter_max;
+    for (int i = 0; i < 4; i++) p.nlp_tol[i] = c.nlp_tol[i];
     p.slots_per_stage = B2Off(h->M).total;
     p.dt = c.tf / c.N; p.dt2h = 0.5 * p.dt * p.dt;
     const double lm_s = c.lm_scaled_by_dt ? p.dt * c.lm : c.lm;   // acados-version dependent
@@ -112,6 +118,7 @@ static void fill_params(b2mpc* h)
     p.X = h->f[B2MPC_X]; p.U = h->f[B2MPC_U]; p.SL = h->f[B2MPC_SL]; p.SU = h->f[B2MPC_SU];
     p.PI = h->f[B2MPC_PI]; p.LAM = h->f[B2MPC_LAM]; p.T = h->f[B2MPC_T]; p.STATS = h->f[B2MPC_STATS];
     p.STATUS = h->fi[B2MPC_STATUS]; p.QP_ITER = h->fi[B2MPC_QP_ITER]; p.QP_STATUS = h->fi[B2MPC_QP_STATUS];
+    p.NLP_RES = h->f[B2MPC_NLP_RES]; p.SQP_ITER = h->fi[B2MPC_SQP_ITER];
     p.WS = h->ws;
 }
 
@@ -125,6 +132,9 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     if (!(cfg->tf > 0.0)) return fail(B2MPC_EINVAL, "tf must be > 0");
     if (cfg->integrator != 0 && cfg->integrator != 1) return fail(B2MPC_EINVAL, "integrator must be 0 (IRK-GL4) or 1 (RK4)");
     if (cfg->qp_iter_max < 1) return fail(B2MPC_EINVAL, "qp_iter_max must be >= 1");
+    if (cfg->nlp_solver != 0 && cfg->nlp_solver != 1) return fail(B2MPC_EINVAL, "nlp_solver must be 0 (SQP_RTI) or 1 (SQP)");
+    if (cfg->nlp_solver == 1 && cfg->nlp_iter_max < 1) return fail(B2MPC_EINVAL, "nlp_iter_max must be >= 1");
+    if (cfg->nlp_solver == 1 && cfg->kernel == 1) return fail(B2MPC_EINVAL, "the SQP loop needs a warp-per-problem kernel (kernel 0, 2 or 3)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(B2MPC_ENODEV, "no CUDA device: libb200mpc has no CPU fallback");
@@ -140,7 +150,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     h->len[B2MPC_X] = (int64_t)(N + 1) * 5; h->len[B2MPC_U] = (int64_t)N * 2; h->len[B2MPC_PI] = (int64_t)N * 5;
     h->len[B2MPC_LAM] = h->len[B2MPC_T] = (int64_t)(N + 1) * h->nct;
     h->len[B2MPC_STATS] = 8; h->len[B2MPC_GOAL] = 2; h->len[B2MPC_OBST] = (int64_t)M * 4;
-    h->len[B2MPC_MARGIN] = 2; h->len[B2MPC_U0] = 2;
+    h->len[B2MPC_MARGIN] = 2; h->len[B2MPC_U0] = 2; h->len[B2MPC_NLP_RES] = 4;
     int64_t maxlen = 0;
     for (int i = 0; i < B2MPC_N_FIELDS; i++) {
         if (h->len[i] > maxlen) maxlen = h->len[i];
@@ -176,12 +186,14 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
             return fail(B2MPC_EINVAL, "all-shared warp kernel needs %zu B > %d B of shared memory", b2_wpp_smem_bytes(N, M, smask), max_smem);
         }
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED>;
+        h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED, true>;
         h->kernel = 3;
     } else if (cfg->kernel == 1) {
         h->kernel = 1;
     } else {
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL>
                   : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_ALL_GLOBAL> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
+        h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL, true>;
         h->kernel = 2;
     }
     // global scratch of the thread-per-problem kernel
@@ -197,8 +209,12 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 2 * B2_ORDER_MAXKEYS + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
         cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
-        int occ = 0, sms = 0;
+        int occ = 0, sms = 0, occ_q = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, h->wpp_fn_sqp, 32, h->wpp_smem);
+        if (occ_q < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "SQP warp kernel does not fit an SM"); }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->wpp_fn, 32, h->wpp_smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         if (occ < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "warp kernel does not fit an SM"); }
@@ -398,7 +414,8 @@ __global__ void b2_prepare_slack(const double* __restrict__ X0, const double* __
 }
 // ocp_solver.reset() + set_initial_guess(), robot_ocp_problem.py:286-306 (incl. aliasing quirk :301-302)
 __global__ void b2_reset(double* __restrict__ X0, double* __restrict__ X, double* __restrict__ U, double* __restrict__ SL,
-                         double* __restrict__ SU, const uint8_t* __restrict__ mask, int N, int M, int B, int Bm)
+                         double* __restrict__ SU, double* __restrict__ PI, double* __restrict__ LAM, double* __restrict__ T,
+                         const uint8_t* __restrict__ mask, int N, int M, int B, int Bm)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -410,6 +427,10 @@ __global__ void b2_reset(double* __restrict__ X0, double* __restrict__ X, double
         for (int i = 0; i < 5; i++) X[((size_t)k * 5 + i) * Bm + b] = x0[i];
         if (k < N) { U[((size_t)k * 2) * Bm + b] = 0.0; U[((size_t)k * 2 + 1) * Bm + b] = 0.0; }
         for (int j = 0; j < M; j++) { SL[((size_t)k * M + j) * Bm + b] = 0.0; SU[((size_t)k * M + j) * Bm + b] = 0.0; }
+        // reset() also forgets the multipliers (they only matter to the full-SQP mode's first convergence test)
+        if (k < N) for (int i = 0; i < 5; i++) PI[((size_t)k * 5 + i) * Bm + b] = 0.0;
+        const int nct = 12 + 4 * M;
+        for (int i = 0; i < nct; i++) { LAM[((size_t)k * nct + i) * Bm + b] = 0.0; T[((size_t)k * nct + i) * Bm + b] = 0.0; }
     }
 }
 // ocp_integrator: X0 <- F(X0, U[0]), robot_ocp_problem.py:207-212 (same IRK as the OCP, :136)
@@ -451,7 +472,8 @@ extern "C" int b2mpc_reset(b2mpc* h, const uint8_t* dmask, int64_t batch, void* 
     int rc = check_batch(h, batch);
     if (rc) return rc;
     b2_reset<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        h->f[B2MPC_X0], h->f[B2MPC_X], h->f[B2MPC_U], h->f[B2MPC_SL], h->f[B2MPC_SU], dmask, h->N, h->M, (int)batch, h->Bm);
+        h->f[B2MPC_X0], h->f[B2MPC_X], h->f[B2MPC_U], h->f[B2MPC_SL], h->f[B2MPC_SU], h->f[B2MPC_PI], h->f[B2MPC_LAM], h->f[B2MPC_T],
+        dmask, h->N, h->M, (int)batch, h->Bm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;
@@ -670,13 +692,18 @@ __global__ void b2_order_scatter(const int32_t* __restrict__ key, const int32_t*
 }
 
 // ------------------------------------------------------------------ the solve
-extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
+static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const double* tol4, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    if (sqp && h->kernel == 1) return fail(B2MPC_EINVAL, "the SQP loop needs a warp-per-problem kernel (kernel 0, 2 or 3)");
     cudaStream_t st = (cudaStream_t)stream;
     B2Params p = h->prm;
     p.B = (int)batch;
+    if (sqp) {
+        if (max_iter > 0) p.nlp_iter_max = max_iter;
+        if (tol4) for (int i = 0; i < 4; i++) p.nlp_tol[i] = tol4[i];
+    }
     if (h->kernel != 1) {
         // order buffer: [order (Bm) | key (Bm) | hist (MAXKEYS) | fill (MAXKEYS) | work counter]
         int32_t* key = h->order + h->Bm;
@@ -690,7 +717,10 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
         h->launches += 2;
         p.ORDER = h->order;
         p.NEXT = next;
-        if (h->wpp_fn_small && batch <= h->small_batch_max) {
+        if (sqp) {
+            const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);
+            h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem, st>>>(p);
+        } else if (h->wpp_fn_small && batch <= h->small_batch_max) {
             h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
         } else {
             const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);   // persistent: one warp-CTA per resident slot
@@ -705,6 +735,16 @@ extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;
+}
+extern "C" int b2mpc_solve(b2mpc* h, int64_t batch, void* stream)
+{
+    if (!h) return fail(B2MPC_EINVAL, "null handle");
+    return solve_impl(h, batch, h->cfg.nlp_solver == 1, 0, nullptr, stream);
+}
+extern "C" int b2mpc_solve_sqp(b2mpc* h, int64_t batch, int32_t max_iter, const double* tol4, void* stream)
+{
+    if (!h) return fail(B2MPC_EINVAL, "null handle");
+    return solve_impl(h, batch, true, max_iter, tol4, stream);
 }
 
 extern "C" int b2mpc_solve_host(b2mpc* h, int64_t batch, const double* x0, const double* p, const double* yref,

@@ -45,6 +45,8 @@ struct B2Params {
     int32_t N, M, B, Bm;         // horizon, obstacles, batch in this launch, row stride (= max_batch)
     int32_t integrator, qp_iter_max, pred_corr, cond_pred_corr, itref_corr_max;
     int32_t nct;                 // padded constraints per node = 12 + 4M
+    int32_t nlp_iter_max;        // full-SQP mode: QP limit and the four residual tolerances
+    double nlp_tol[4];
     int32_t slots_per_stage;
     double dt, dt2h;             // h, h*h/2
     double Hd[7], Hde[7];        // Hessian diagonals (stage / terminal), LM included
@@ -60,6 +62,8 @@ struct B2Params {
     // outputs
     double *PI, *LAM, *T, *STATS;
     int32_t *STATUS, *QP_ITER, *QP_STATUS;
+    double* NLP_RES;             // full-SQP mode outputs
+    int32_t* SQP_ITER;
     const int32_t* ORDER;        // optional launch order of the problems (warp kernel)
     int32_t* NEXT;               // work counter of the persistent warp kernel (zeroed before each launch)
     // scratch

@@ -120,7 +120,7 @@ __device__ __forceinline__ double b2_bcast(double v, int src) { return __shfl_sy
 // expansion modes
 enum { XP_SOLVE = 0, XP_REFINE = 1, XP_UPDATE = 2, XP_LIN = 3 };
 
-template <int MT, int NT, unsigned SMASK>
+template <int MT, int NT, unsigned SMASK, bool SQP = false>
 struct WppSolver {
     const B2Params& p;
     const int b, lane, N, NS, GS, M, nct;
@@ -902,12 +902,90 @@ struct WppSolver {
         __syncwarp();
     }
 
-    // ---- the whole RTI call -------------------------------------------------------------------------
+    // ---- full-SQP mode only: KKT residuals of the NLP at the current iterate with the multipliers of the previous
+    // QP (PI, LAM, T in global memory), i.e. acados' ocp_nlp_res_compute: [stationarity, dynamics gap,
+    // g_i - t_i incl. the x0 embedding, lam_i t_i] as infinity norms.  Runs right after prepare_and_init(), whose
+    // linearisation (sv, b, g, cx, cy, lg, ug, ...) is everything it needs: node-parallel, one pass.
+    __device__ void nlp_residuals(double res[4])
+    {
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+        for (k = lane; k <= N; k += 32) {
+            const double* lk = p.LAM + ((size_t)k * nct) * Bm + b;
+            const double* tk = p.T + ((size_t)k * nct) * Bm + b;
+            double rg[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) rg[i] = Q<PF_G>(i);
+            if (k < N) {
+                double sv[10], pk[5], bt[7];
+#pragma unroll
+                for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, k);
+#pragma unroll
+                for (int i = 0; i < 5; i++) { pk[i] = p.PI[((size_t)k * 5 + i) * Bm + b]; n1 = fmax(n1, fabs(Q<PF_B>(i))); }
+                b2_bat_mul(sv, p.dt, p.dt2h, pk, bt);
+#pragma unroll
+                for (int i = 0; i < 7; i++) rg[i] += bt[i];
+            }
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) rg[2 + i] -= p.PI[((size_t)(k - 1) * 5 + i) * Bm + b];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; i++) n2 = fmax(n2, fabs(p.X0[(size_t)i * Bm + b] - p.X[(size_t)i * Bm + b]));
+            }
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                double lb, ub;
+                box_bounds(s, lb, ub);
+                const double ll = lk[(size_t)(o_lb + s) * Bm], lu_ = lk[(size_t)(o_ub + s) * Bm];
+                const double tl = tk[(size_t)(o_lb + s) * Bm], tu = tk[(size_t)(o_ub + s) * Bm];
+                rg[b2_slot2v(s)] += lu_ - ll;
+                n2 = fmax(n2, fmax(fabs(-lb - tl), fabs(ub - tu)));
+                n3 = fmax(n3, fmax(fabs(ll * tl), fabs(lu_ * tu)));
+            }
+            const double sc = scal(k);
+#pragma unroll JU
+            for (int j = 0; j < M; j++) {
+                const double l0 = lk[(size_t)(o_lg + j) * Bm], l1 = lk[(size_t)(o_ug + j) * Bm];
+                const double l2 = lk[(size_t)(o_ls + j) * Bm], l3 = lk[(size_t)(o_us + j) * Bm];
+                const double t0 = tk[(size_t)(o_lg + j) * Bm], t1 = tk[(size_t)(o_ug + j) * Bm];
+                const double t2 = tk[(size_t)(o_ls + j) * Bm], t3 = tk[(size_t)(o_us + j) * Bm];
+                const double dl = l1 - l0;
+                rg[2] += Q<PF_CX>(j) * dl; rg[3] += Q<PF_CY>(j) * dl;
+                const double sli = Q<PF_SLI>(j), sui = Q<PF_SUI>(j);
+                const double gsl = Q<PF_ZLQ>(j) - l0 - l2;
+                const double gsu = sc * (p.zu + p.Zu * sui) - l1 - l3;
+                n0 = fmax(n0, fmax(fabs(gsl), fabs(gsu)));
+                // lg = lh - h - sl, ug = uh - h + su  =>  h + sl - lh = -lg,  uh - h + su = ug
+                n2 = fmax(n2, fmax(fmax(fabs(-Q<PF_LG>(j) - t0), fabs(Q<PF_UG>(j) - t1)), fmax(fabs(sli - t2), fabs(sui - t3))));
+                n3 = fmax(n3, fmax(fmax(fabs(l0 * t0), fabs(l1 * t1)), fmax(fabs(l2 * t2), fabs(l3 * t3))));
+            }
+            if (k == 0) { rg[2] = rg[3] = rg[4] = rg[5] = rg[6] = 0.0; }       // x_0 is fixed by the embedding
+            if (k == N) { rg[0] = rg[1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) n0 = fmax(n0, fabs(rg[i]));
+        }
+        res[0] = b2_warp_max_nonneg(n0); res[1] = b2_warp_max_nonneg(n1); res[2] = b2_warp_max_nonneg(n2); res[3] = b2_warp_max_nonneg(n3);
+    }
+
+    // ---- the whole call: one RTI iteration (SQP = false, the reference: nlp_solver_type 'SQP_RTI',
+    // robot_ocp_problem.py:130), or acados' full `SQP` loop with FIXED_STEP globalisation (SQP = true:
+    // [linearise -> NLP residuals -> convergence test -> QP -> full step] up to nlp_iter_max QPs, the iterate
+    // and the multipliers going through global memory between the iterations; status 0 converged, 2 max_iter,
+    // 4 QP failure).  Every problem leaves the loop at its own iteration: the CTA pulls the next one.
     __device__ void run()
     {
+        int sqp_it = 0, qp_total = 0, status = 0, qs = 0, n_itref = 0;
+        double nres[4] = {0.0, 0.0, 0.0, 0.0};
+        for (;;) {
         prepare_and_init();
+        if (SQP) {
+            nlp_residuals(nres);
+            if (nres[0] < p.nlp_tol[0] && nres[1] < p.nlp_tol[1] && nres[2] < p.nlp_tol[2] && nres[3] < p.nlp_tol[3]) { status = 0; break; }
+            if (sqp_it >= p.nlp_iter_max) { status = 2; break; }
+        }
         alpha = 1.0;
-        int kk = 0, n_itref = 0;
+        int kk = 0;
         const double inv_nc = 1.0 / nc;
         double a = 0.0;
         for (;; kk++) {
@@ -943,12 +1021,12 @@ struct WppSolver {
             a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         }
-        int qs;
         if (kk == p.qp_iter_max) qs = 1;
         else if (alpha <= p.alpha_min) qs = 2;
         else if (mu != mu || nrm[0] != nrm[0] || nrm[1] != nrm[1] || nrm[2] != nrm[2] || nrm[3] != nrm[3]) qs = 3;
         else qs = 0;
-        const int status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate untouched
+        status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate untouched
+        qp_total += kk;
         for (k = lane; k <= N; k += 32) {
             if (status == 0) {
 #pragma unroll
@@ -972,16 +1050,24 @@ struct WppSolver {
                 p.T[((size_t)k * nct + i) * Bm + b] = Q<PF_T>(i);
             }
         }
+        sqp_it++;
+        __syncwarp();                                          // the next linearisation reads what other lanes wrote
+        if (!SQP || status != 0) break;
+        }
         if (lane == 0) {
-            p.STATUS[b] = status; p.QP_ITER[b] = kk; p.QP_STATUS[b] = qs;
+            p.STATUS[b] = status; p.QP_ITER[b] = qp_total; p.QP_STATUS[b] = qs;
             p.STATS[0 * Bm + b] = nrm[0]; p.STATS[1 * Bm + b] = nrm[1]; p.STATS[2 * Bm + b] = nrm[2]; p.STATS[3 * Bm + b] = nrm[3];
             p.STATS[4 * Bm + b] = mu; p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
+            if (SQP) {
+                p.SQP_ITER[b] = sqp_it;
+                p.NLP_RES[0 * Bm + b] = nres[0]; p.NLP_RES[1 * Bm + b] = nres[1]; p.NLP_RES[2 * Bm + b] = nres[2]; p.NLP_RES[3 * Bm + b] = nres[3];
+            }
         }
         __syncwarp();
     }
 };
 
-template <int MT, int NT, unsigned SMASK>
+template <int MT, int NT, unsigned SMASK, bool SQP = false>
 __global__ void __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_SHARED) ? B2_WPP_MINB : 1) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
@@ -992,7 +1078,7 @@ __global__ void __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= p.B) break;
         const int b = p.ORDER ? p.ORDER[i] : i;      // expensive problems first (shorter tail), see b2_order_problems
-        WppSolver<MT, NT, SMASK> s(p, b, b2_smem, gm);
+        WppSolver<MT, NT, SMASK, SQP> s(p, b, b2_smem, gm);
         s.run();
     }
 }

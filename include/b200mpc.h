@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B2MPC_ABI_VERSION 1
+#define B2MPC_ABI_VERSION 2
 #define B2MPC_MAX_OBST 32
 #define B2MPC_MAX_N 128
 
@@ -60,6 +60,11 @@ typedef struct b2mpc_config {
     double zu, Zu;           /* cost.zu/Zu (upper-side slack penalty), :118-122 */
     double mu0, alpha_min, res_g_max, res_b_max, res_d_max, res_m_max;   /* HPIPM */
     double reg_prim, lam_min, t_min, tau_min, thr0;                      /* HPIPM */
+    /* outer loop of b2mpc_solve: 0 = 'SQP_RTI' (the reference, solver_options.nlp_solver_type, :130),
+     * 1 = acados 'SQP' (full steps until the NLP residuals pass nlp_tol or nlp_iter_max QPs were solved) */
+    int32_t nlp_solver;
+    int32_t nlp_iter_max;    /* solver_options.nlp_solver_max_iter (acados default 100); SQP only */
+    double nlp_tol[4];       /* nlp_solver_tol_stat / _eq / _ineq / _comp (acados default 1e-6 each); SQP only */
 } b2mpc_config;
 
 /* fields of b2mpc_set / b2mpc_get; len = doubles per problem */
@@ -73,22 +78,24 @@ enum {
     B2MPC_U = 6,      /* [N*2]          set/get(i,'u'), :140,198,255,258,305                 */
     B2MPC_SL = 7,     /* [(N+1)*M]      get(i,'sl') (lower slack iterate; reset() zeroes)    */
     B2MPC_SU = 8,     /* [(N+1)*M]      get(i,'su')                                          */
-    B2MPC_PI = 9,     /* [N*5]          get(i,'pi')  (output only)                           */
-    B2MPC_LAM = 10,   /* [(N+1)*(12+4M)] get(i,'lam') padded [lb6 lg ub6 ug ls us] (output)  */
-    B2MPC_T = 11,     /* [(N+1)*(12+4M)] get(i,'t')   (output)                               */
+    B2MPC_PI = 9,     /* [N*5]          get(i,'pi')  (output; SQP: in/out, reset() zeroes)   */
+    B2MPC_LAM = 10,   /* [(N+1)*(12+4M)] get(i,'lam') padded [lb6 lg ub6 ug ls us] (same)    */
+    B2MPC_T = 11,     /* [(N+1)*(12+4M)] get(i,'t')   (same)                                 */
     B2MPC_STATS = 12, /* [8] res_g,res_b,res_d,res_m,mu,alpha,n_itref,0 at exit (output)     */
     B2MPC_GOAL = 13,  /* [2]            sub-goal used by b2mpc_prepare_slack / closed loop   */
     B2MPC_OBST = 14,  /* [M*4]          obstacle states (x,y,vx,vy), visualization.py:10-18  */
     B2MPC_MARGIN = 15, /* [2]           closed loop: min_margin_traj, distance_to_goal (:222-228,:246) */
     B2MPC_U0 = 16,    /* [2]            control applied by the last b2mpc_loop_post (get(0,'u'), :198) */
-    B2MPC_N_FIELDS = 17
+    B2MPC_NLP_RES = 17, /* [4]          SQP: res_stat,res_eq,res_ineq,res_comp at exit (get_residuals()) */
+    B2MPC_N_FIELDS = 18
 };
 enum { B2MPC_STATUS = 0, B2MPC_QP_ITER = 1, B2MPC_QP_STATUS = 2,
        B2MPC_STEPS = 3,   /* closed loop: control steps taken (i of :184-260) */
        B2MPC_DONE = 4,    /* closed loop: reached the goal tolerance (reached_subgoal, :247-250) */
        B2MPC_OOB = 5,     /* closed loop: left the arena at least once (:213-214) */
        B2MPC_NFAIL = 6,   /* closed loop: number of status-4 solves (:203) */
-       B2MPC_N_IFIELDS = 7 };
+       B2MPC_SQP_ITER = 7, /* SQP: QPs solved by the last b2mpc_solve (get_stats('sqp_iter')); QP_ITER then holds their IPM total */
+       B2MPC_N_IFIELDS = 8 };
 enum { B2MPC_LAYOUT_SOA = 0, B2MPC_LAYOUT_AOS = 1 };
 
 enum {
@@ -126,8 +133,13 @@ int b2mpc_prepare_slack(b2mpc *h, int64_t batch, void *stream);
 /* ocp_solver.reset() + set_initial_guess(), :286-306 (mask: uint8 per problem, NULL = all);
  * like the reference it zeroes v,omega of X0 itself (aliasing quirk :301-302) */
 int b2mpc_reset(b2mpc *h, const uint8_t *dmask, int64_t batch, void *stream);
-/* ocp_solver.solve(), :195 -- one SQP_RTI iteration for every problem; fills STATUS, QP_ITER */
+/* ocp_solver.solve(), :195 -- one SQP_RTI iteration for every problem (cfg.nlp_solver = 0); fills STATUS, QP_ITER.
+ * With cfg.nlp_solver = 1 the same launch runs acados' full SQP loop per problem (status 0 converged,
+ * 2 max_iter, 4 QP failure; also fills SQP_ITER, NLP_RES). */
 int b2mpc_solve(b2mpc *h, int64_t batch, void *stream);
+/* full SQP on a handle of either kind (solver.options_set('max_iter'/'tol_*') + solve()): max_iter <= 0 and
+ * tol = NULL take the handle's configuration.  Needs a warp-per-problem kernel (cfg.kernel != 1). */
+int b2mpc_solve_sqp(b2mpc *h, int64_t batch, int32_t max_iter, const double *tol4, void *stream);
 /* ocp_integrator.set/solve/get, :207-212: X0 <- F(X0, U[0]) */
 int b2mpc_sim(b2mpc *h, int64_t batch, void *stream);
 /* warm-start shift, :253-258 */

@@ -1001,6 +1001,145 @@ void orc_rti_solve_batch(const orc_config *c, int64_t B, int nthreads,
     for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
 }
 
+/* ------------------------------------------------------------ full SQP mode */
+/* north_star kernel 4 ("SQP outer loop with convergence test").  The reference itself never runs it
+ * (nlp_solver_type = 'SQP_RTI', robot_ocp_problem.py:130): this follows acados' `SQP` solver as published
+ * (ocp_nlp_sqp: linearise -> NLP residuals -> convergence test -> QP -> full step, FIXED_STEP globalisation,
+ * tolerances nlp_solver_tol_{stat,eq,ineq,comp}), restated from memory like the rest of this file. */
+
+/* KKT residuals of the NLP at (x,u,sl,su) with multipliers (pi, lam, t) in the padded layout of
+ * orc_rti_solve: res = [stationarity, dynamics gap, inequality residual g_i - t_i (incl. the x0 embedding),
+ * complementarity lam_i t_i], infinity norms.  Written directly from the model functions (no QP data). */
+void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p,
+                       const double *yref, const double *zl, const double *Zl,
+                       const double *x, const double *u, const double *sl, const double *su,
+                       const double *pi, const double *lam, const double *t, double res[4])
+{
+    const int N = c->N, M = c->M, nct = 12 + 4 * M;
+    const double dt = c->tf / N;
+    static const int idxbx[4] = {0, 1, 3, 4};
+    double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (int i = 0; i < NX; i++) r2 = fmax(r2, fabs(x0bar[i] - x[i]));
+    for (int k = 0; k <= N; k++) {
+        const double *xk = x + k * NX, *uk = u + k * NU, *yr = yref + k * ORC_NY;
+        const double *lk = lam + (size_t)k * nct, *tk = t + (size_t)k * nct;
+        const double scal = k < N ? dt : 1.0;
+        double gu[NU] = {0, 0}, gx[NX] = {0, 0, 0, 0, 0};
+        if (k < N) {
+            double A[25], Bm[10], xn[5];
+            if (c->integrator == 1) orc_rk4_step(xk, uk, dt, xn, A, Bm);
+            else orc_gl4_step(xk, uk, dt, xn, A, Bm);
+            const double *pk = pi + k * NX;
+            for (int r = 0; r < NX; r++) {
+                r1 = fmax(r1, fabs(xn[r] - x[(k + 1) * NX + r]));
+                for (int j = 0; j < NU; j++) gu[j] += Bm[r * 2 + j] * pk[r];
+                for (int j = 0; j < NX; j++) gx[j] += A[r * 5 + j] * pk[r];
+            }
+            for (int j = 0; j < NU; j++) gu[j] += scal * c->W[4 + j] * (uk[j] - yr[4 + j]);
+            for (int j = 0; j < 4; j++) gx[idxbx[j]] += scal * c->W[j] * (xk[idxbx[j]] - yr[j]);
+        } else {
+            for (int j = 0; j < 4; j++) gx[idxbx[j]] += c->We[j] * (xk[idxbx[j]] - yr[j]);
+        }
+        if (k > 0) for (int j = 0; j < NX; j++) gx[j] -= pi[(k - 1) * NX + j];
+        /* boxes: slots [u0,u1,x,y,v,w]; lower at lk[slot], upper at lk[6+M+slot] */
+        for (int s = 0; s < 6; s++) {
+            const int on = s < 2 ? (k < N) : (k > 0 && k < N);
+            if (!on) continue;
+            const double val = s < 2 ? uk[s] : xk[idxbx[s - 2]];
+            const double lo = s < 2 ? c->lbu[s] : c->lbx[s - 2], hi = s < 2 ? c->ubu[s] : c->ubx[s - 2];
+            const double ll = lk[s], lu = lk[6 + M + s], tl = tk[s], tu = tk[6 + M + s];
+            if (s < 2) gu[s] += lu - ll; else gx[idxbx[s - 2]] += lu - ll;
+            r2 = fmax(r2, fmax(fabs(val - lo - tl), fabs(hi - val - tu)));
+            r3 = fmax(r3, fmax(fabs(ll * tl), fabs(lu * tu)));
+        }
+        double hh[MM], cx[MM], cy[MM];
+        orc_con_h(xk, p + (size_t)k * 2 * M, M, c->r2, hh, cx, cy);
+        for (int j = 0; j < M; j++) {
+            const double s_l = c->soft ? sl[k * M + j] : 0.0, s_u = c->soft ? su[k * M + j] : 0.0;
+            const double l0 = lk[6 + j], l1 = lk[12 + M + j], t0 = tk[6 + j], t1 = tk[12 + M + j];
+            gx[0] += cx[j] * (l1 - l0); gx[1] += cy[j] * (l1 - l0);
+            r2 = fmax(r2, fmax(fabs(hh[j] + s_l - c->lh - t0), fabs(c->uh - hh[j] + s_u - t1)));
+            r3 = fmax(r3, fmax(fabs(l0 * t0), fabs(l1 * t1)));
+            if (c->soft) {
+                const double l2 = lk[12 + 2 * M + j], l3 = lk[12 + 3 * M + j], t2 = tk[12 + 2 * M + j], t3 = tk[12 + 3 * M + j];
+                const double gsl = scal * (zl[k * M + j] + Zl[k * M + j] * s_l) - l0 - l2;
+                const double gsu = scal * (c->zu + c->Zu * s_u) - l1 - l3;
+                r0 = fmax(r0, fmax(fabs(gsl), fabs(gsu)));
+                r2 = fmax(r2, fmax(fabs(s_l - t2), fabs(s_u - t3)));
+                r3 = fmax(r3, fmax(fabs(l2 * t2), fabs(l3 * t3)));
+            }
+        }
+        if (k < N) for (int j = 0; j < NU; j++) r0 = fmax(r0, fabs(gu[j]));
+        if (k > 0) for (int j = 0; j < NX; j++) r0 = fmax(r0, fabs(gx[j]));      /* x_0 is fixed by the embedding */
+    }
+    res[0] = r0; res[1] = r1; res[2] = r2; res[3] = r3;
+}
+
+/* SQP with full steps: returns acados status 0 (converged), 2 (max_iter), 4 (QP failure).
+ * pi/lam/t are IN/OUT (multipliers of the previous call or zeros); *sqp_iter = QPs solved, *qp_iter = their
+ * interior-point iterations in total, res[4] = NLP residuals at exit. */
+int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4],
+                  const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
+                  double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
+                  int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats)
+{
+    int it = 0, qtot = 0, status;
+    double r[4], st8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (;; it++) {
+        orc_nlp_residuals(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, r);
+        if (r[0] < tol[0] && r[1] < tol[1] && r[2] < tol[2] && r[3] < tol[3]) { status = 0; break; }
+        if (it >= max_iter) { status = 2; break; }
+        int32_t qi = 0, qs = 0;
+        const int s = orc_rti_solve(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, &qi, &qs, st8);
+        qtot += qi;
+        if (s != 0) { status = s; it++; break; }
+    }
+    if (sqp_iter) *sqp_iter = it;
+    if (qp_iter) *qp_iter = qtot;
+    if (res) memcpy(res, r, sizeof(r));
+    if (stats) memcpy(stats, st8, sizeof(st8));
+    return status;
+}
+
+typedef struct {
+    const orc_config *c; int64_t B; atomic_llong next; int max_iter; const double *tol;
+    const double *x0bar, *p, *yref, *zl, *Zl;
+    double *x, *u, *sl, *su, *pi, *lam, *t; int32_t *status, *sqp_iter, *qp_iter; double *res;
+} sqp_job;
+
+static void *sqp_worker(void *arg)
+{
+    sqp_job *j = (sqp_job *)arg;
+    const orc_config *c = j->c;
+    const int N = c->N, M = c->M;
+    const size_t nxs = (size_t)(N + 1) * NX, nus = (size_t)N * NU, nss = (size_t)(N + 1) * M;
+    const size_t nps = (size_t)(N + 1) * 2 * M, nys = (size_t)(N + 1) * ORC_NY, nls = (size_t)(N + 1) * (12 + 4 * M);
+    for (;;) {
+        long long b = atomic_fetch_add(&j->next, 1);
+        if (b >= j->B) break;
+        int32_t it = 0, qi = 0;
+        int s = orc_sqp_solve(c, j->max_iter, j->tol, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
+                              j->zl + b * nss, j->Zl + b * nss, j->x + b * nxs, j->u + b * nus, j->sl + b * nss, j->su + b * nss,
+                              j->pi + b * (size_t)N * NX, j->lam + b * nls, j->t + b * nls, &it, &qi, j->res + b * 4, NULL);
+        j->status[b] = s; j->sqp_iter[b] = it; j->qp_iter[b] = qi;
+    }
+    return NULL;
+}
+
+void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4],
+                         const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
+                         double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
+                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res)
+{
+    sqp_job j = {c, B, 0, max_iter, tol, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, status, sqp_iter, qp_iter, res};
+    atomic_init(&j.next, 0);
+    if (nthreads <= 1) { sqp_worker(&j); return; }
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, sqp_worker, &j);
+    for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+}
+
 /* ------------------------------------------------------- validation exports */
 int orc_export_qp(const orc_config *c, const double *x0bar, const double *p,
                   const double *yref, const double *zl, const double *Zl,

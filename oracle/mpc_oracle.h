@@ -95,6 +95,23 @@ void orc_rti_solve_batch(const orc_config *c, int64_t B, int nthreads,
                          double *x, double *u, double *sl, double *su,
                          int32_t *status, int32_t *qp_iter, double *stats);
 
+/* ---- full SQP mode (north_star kernel 4; the reference itself runs SQP_RTI only, :130) ---- */
+/* res[4] = inf norms of [stationarity, dynamics gap, g_i - t_i (incl. |x0bar - x_0|), lam_i t_i] */
+void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p,
+                       const double *yref, const double *zl, const double *Zl,
+                       const double *x, const double *u, const double *sl, const double *su,
+                       const double *pi, const double *lam, const double *t, double res[4]);
+/* acados `SQP` with FIXED_STEP: [residuals -> test against tol[4] -> QP -> full step] up to max_iter QPs.
+ * pi/lam/t in/out (previous multipliers or zeros).  Returns 0 converged, 2 max_iter, 4 QP failure. */
+int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4],
+                  const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
+                  double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
+                  int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats);
+void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4],
+                         const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
+                         double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
+                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res);
+
 /* ---- QP export for validation (tests only) ------------------------------ */
 /* Builds the RTI QP of one problem and returns it densely so that numpy can
  * assemble the KKT system independently. Layout documented in pyoracle.py. */

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/b200mpc.h but not exported"
     assert set(capi.EXPORTS) <= names
-    assert lib.b2mpc_abi_version() == 1
+    assert lib.b2mpc_abi_version() == 2
 
 
 def test_default_config_matches_reference_constants(lib):
@@ -38,12 +38,15 @@ def test_default_config_matches_reference_constants(lib):
     assert abs(c.r2 - 2.4 ** 2) < 1e-15 and c.lh == 0.0 and c.uh == 1e5                   # robot_model.py:62, :99-103
     assert (c.mu0, c.alpha_min, c.res_g_max, c.res_b_max) == (1.0, 1e-8, 1e-6, 1e-8)      # acados' HPIPM block
     assert c.lm_scaled_by_dt == 1 and c.pred_corr == 1 and c.cond_pred_corr == 1 and c.itref_corr_max == 2
+    assert c.nlp_solver == 0                                                              # 'SQP_RTI', :130
+    assert c.nlp_iter_max == 100 and list(c.nlp_tol) == [1e-6] * 4                        # acados defaults (SQP mode)
 
 
 def test_create_validates_arguments_and_has_no_cpu_fallback(lib):
     import torch
     h = C.c_void_p()
-    for bad in (dict(N=0), dict(N=129), dict(n_obst=0), dict(n_obst=33), dict(max_batch=0), dict(tf=0.0), dict(integrator=7)):
+    for bad in (dict(N=0), dict(N=129), dict(n_obst=0), dict(n_obst=33), dict(max_batch=0), dict(tf=0.0), dict(integrator=7),
+                dict(nlp_solver=2), dict(nlp_solver=1, nlp_iter_max=0), dict(nlp_solver=1, kernel=1)):
         c = capi.default_config(20, 5, 2.0, 8, 0)
         for k, v in bad.items():
             setattr(c, k, v)

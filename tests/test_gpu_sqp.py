@@ -1,0 +1,115 @@
+"""GPU tests of the full-SQP mode (north_star kernel 4: SQP outer loop + convergence test fused into the persistent
+warp kernel), through the C-ABI, against the oracle's SQP loop on identical seeded inputs.  The reference itself
+runs SQP_RTI (robot_ocp_problem.py:130); the one-iteration case ties the SQP kernel to the RTI kernel bit for bit."""
+import numpy as np
+import pytest
+
+from b200mpc import world
+
+pytestmark = pytest.mark.gpu
+DIMS = world.MpcDims(20, 5, 2.0)
+FIELDS = ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch
+
+
+def _load(torch, solver, sc, B):
+    for name in FIELDS:
+        solver.set(name, torch.from_numpy(sc[name]).cuda())
+    solver.reset_multipliers(B)
+
+
+def _read(solver, B):
+    out = {k: solver.get(k, B).cpu().numpy() for k in ("x", "u", "sl", "su", "pi", "lam", "t", "nlp_res")}
+    for k in ("status", "qp_iter", "sqp_iter"):
+        out[k] = solver.get_int(k, B).cpu().numpy()
+    return out
+
+
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_one_sqp_iteration_is_the_rti_step(torch_cuda, kernel):
+    from b200mpc import BatchedMpcSolver
+    B = 300
+    sc = world.random_scenarios(B, DIMS, seed=12, moving_start=True)
+    s = BatchedMpcSolver(20, 5, 2.0, max_batch=B, kernel=kernel)
+    _load(torch_cuda, s, sc, B)
+    s.solve(B)
+    rti = _read(s, B)
+    _load(torch_cuda, s, sc, B)
+    s.solve_sqp(B, max_iter=1)
+    sqp = _read(s, B)
+    s.close()
+    for k in ("x", "u", "sl", "su", "pi", "lam", "t", "qp_iter"):
+        assert np.array_equal(rti[k], sqp[k]), k
+    assert (sqp["sqp_iter"] == 1).all()
+    assert np.array_equal(sqp["status"] == 4, rti["status"] == 4) and set(np.unique(sqp["status"])) <= {2, 4}
+
+
+@pytest.mark.parametrize("N,M,tf,B,kernel", [(20, 5, 2.0, 192, 0), (20, 5, 2.0, 96, 3), (12, 3, 1.2, 100, 0)])
+def test_sqp_matches_oracle(torch_cuda, oracle, N, M, tf, B, kernel):
+    from b200mpc import BatchedMpcSolver
+    dims = world.MpcDims(N, M, tf)
+    sc = world.random_scenarios(B, dims, seed=14, moving_start=True)
+    max_iter = 250
+    s = BatchedMpcSolver(N, M, tf, max_batch=B, kernel=kernel, nlp_solver=1, nlp_iter_max=max_iter)
+    _load(torch_cuda, s, sc, B)
+    s.solve(B)                                            # cfg.nlp_solver = 1: solve() IS the SQP loop
+    out = _read(s, B)
+    cfg = oracle.default_config(N, M, tf)
+    ref = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    r = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], ref["x"], ref["u"], ref["sl"], ref["su"],
+                               max_iter=max_iter, nthreads=8)
+    conv = (r["status"] == 0) & (out["status"] == 0)
+    assert conv.mean() > 0.5
+    assert np.mean(out["status"] == r["status"]) >= 0.97
+    # every QP of a converging run is warm and well conditioned: same number of SQP iterations up to the +-1 of a
+    # residual that crosses 1e-6 within rounding (linear convergence, ratio ~0.9 per iteration)
+    d = np.abs(out["sqp_iter"] - r["sqp_iter"])[conv]
+    assert np.mean(d == 0) >= 0.9 and np.mean(d > 1) <= 0.03, (np.mean(d == 0), d.max())
+    same = conv & (out["sqp_iter"] == r["sqp_iter"])
+    for k in ("u", "x"):
+        e = np.abs(out[k] - ref[k]).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(ref[k]).reshape(B, -1).max(1))
+        assert e[same].max() < 1e-6, (k, e[same].max())
+        assert e[conv].max() < 1e-4, (k, e[conv].max())      # one iteration more or less at tolerance 1e-6
+    assert (out["nlp_res"][out["status"] == 0] < 1e-6).all()
+    assert (out["sqp_iter"][out["status"] == 2] == max_iter).all()
+    # the reported residuals are the NLP's: recompute them with the oracle from what the GPU returned
+    for b in np.nonzero(out["status"] == 0)[0][:8]:
+        res = oracle.nlp_residuals(cfg, sc["x0"][b], sc["p"][b], sc["yref"][b], sc["zl"][b], sc["Zl"][b],
+                                   out["x"][b], out["u"][b], out["sl"][b], out["su"][b], out["pi"][b], out["lam"][b], out["t"][b])
+        assert np.abs(res - out["nlp_res"][b]).max() < 1e-9
+    # converged problems are fixed points: a second call solves no QP and leaves the iterate alone
+    s.solve(B)
+    again = _read(s, B)
+    ok = out["status"] == 0
+    assert (again["sqp_iter"][ok] == 0).all() and (again["status"][ok] == 0).all()
+    assert np.array_equal(again["x"][ok], out["x"][ok]) and np.array_equal(again["u"][ok], out["u"][ok])
+    s.close()
+
+
+def test_sqp_options_and_errors(torch_cuda):
+    from b200mpc import BatchedMpcSolver, capi
+    B = 64
+    sc = world.random_scenarios(B, DIMS, seed=15)
+    s = BatchedMpcSolver(20, 5, 2.0, max_batch=B)
+    its = []
+    for tol in (1e-2, 1e-4):
+        _load(torch_cuda, s, sc, B)
+        s.solve_sqp(B, max_iter=300, tol=(tol,) * 4)
+        its.append(s.get_int("sqp_iter", B).cpu().numpy())
+        st = s.get_int("status", B).cpu().numpy()
+        assert (s.get("nlp_res", B).cpu().numpy()[st == 0] < tol).all()
+    assert (its[0] <= its[1]).all() and its[0].mean() < its[1].mean()
+    s.close()
+    with pytest.raises(capi.B2mpcError):
+        BatchedMpcSolver(20, 5, 2.0, max_batch=8, kernel=1, nlp_solver=1)      # the cross-check kernel has no SQP loop
+    t = BatchedMpcSolver(20, 5, 2.0, max_batch=8, kernel=1)
+    with pytest.raises(capi.B2mpcError):
+        t.solve_sqp(8)
+    t.close()
