@@ -54,7 +54,8 @@ struct b2mpc {
     double* wpriv;                   // node-private rows of the resident CTAs
     size_t wpriv_bytes;
     void (*wpp_fn_small)(const B2Params);   // auto mode: all-shared instantiation for batches that fit the GPU at once
-    void (*wpp_fn_sqp)(const B2Params);     // full-SQP instantiation (same layout, grid and shared memory as wpp_fn)
+    void (*wpp_fn_sqp)(const B2Params);     // full-SQP instantiation: same grid; its layout adds the merit-weight rows
+    size_t wpp_smem_sqp, wpriv_stride_sqp;
     size_t wpp_smem_small;
     int small_batch_max;
     B2Params prm;
@@ -85,6 +86,8 @@ extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst,
     c->nlp_solver = 0;                                             // 'SQP_RTI', robot_ocp_problem.py:130
     c->nlp_iter_max = 100;                                         // acados defaults for the full-SQP mode
     for (int i = 0; i < 4; i++) c->nlp_tol[i] = 1e-6;
+    c->nlp_globalization = 0;                                      // 'FIXED_STEP'
+    c->ls_alpha_min = 0.05; c->ls_alpha_reduction = 0.7;           // acados line-search defaults
 }
 
 static void fill_params(b2mpc* h)
@@ -96,8 +99,9 @@ static void fill_params(b2mpc* h)
     p.integrator = c.integrator; p.qp_iter_max = c.qp_iter_max;
     p.pred_corr = c.pred_corr; p.cond_pred_corr = c.cond_pred_corr; p.itref_corr_max = c.itref_corr_max;
     p.nct = h->nct;
-    p.nlp_iter_max = c.nlp_iter_max;
+    p.nlp_iter_max = c.nlp_iter_max; p.nlp_globalization = c.nlp_globalization;
     for (int i = 0; i < 4; i++) p.nlp_tol[i] = c.nlp_tol[i];
+    p.ls_alpha_min = c.ls_alpha_min; p.ls_alpha_red = c.ls_alpha_reduction;
     p.slots_per_stage = B2Off(h->M).total;
     p.dt = c.tf / c.N; p.dt2h = 0.5 * p.dt * p.dt;
     const double lm_s = c.lm_scaled_by_dt ? p.dt * c.lm : c.lm;   // acados-version dependent
@@ -135,6 +139,9 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     if (cfg->nlp_solver != 0 && cfg->nlp_solver != 1) return fail(B2MPC_EINVAL, "nlp_solver must be 0 (SQP_RTI) or 1 (SQP)");
     if (cfg->nlp_solver == 1 && cfg->nlp_iter_max < 1) return fail(B2MPC_EINVAL, "nlp_iter_max must be >= 1");
     if (cfg->nlp_solver == 1 && cfg->kernel == 1) return fail(B2MPC_EINVAL, "the SQP loop needs a warp-per-problem kernel (kernel 0, 2 or 3)");
+    if (cfg->nlp_globalization != 0 && cfg->nlp_globalization != 1) return fail(B2MPC_EINVAL, "nlp_globalization must be 0 (FIXED_STEP) or 1 (MERIT_BACKTRACKING)");
+    if (cfg->nlp_globalization == 1 && !(cfg->ls_alpha_min > 0.0 && cfg->ls_alpha_min <= 1.0 && cfg->ls_alpha_reduction > 0.0 && cfg->ls_alpha_reduction < 1.0))
+        return fail(B2MPC_EINVAL, "line search needs 0 < ls_alpha_min <= 1 and 0 < ls_alpha_reduction < 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(B2MPC_ENODEV, "no CUDA device: libb200mpc has no CPU fallback");
@@ -205,23 +212,25 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     h->prm.WS = h->ws;
     if (h->kernel != 1) {
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
-        if (h->wpp_smem > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
+        h->wpp_smem_sqp = b2_wpp_smem_bytes(N, M, smask, true);
+        if (h->wpp_smem_sqp > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
         if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 2 * B2_ORDER_MAXKEYS + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
         cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem_sqp);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
         int occ = 0, sms = 0, occ_q = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, h->wpp_fn_sqp, 32, h->wpp_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, h->wpp_fn_sqp, 32, h->wpp_smem_sqp);
         if (occ_q < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "SQP warp kernel does not fit an SM"); }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->wpp_fn, 32, h->wpp_smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         if (occ < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "warp kernel does not fit an SM"); }
         h->wpp_grid = occ * sms;
         if (h->wpp_grid > h->Bm) h->wpp_grid = h->Bm;
-        h->prm.wpriv_stride = b2_wpp_priv_doubles(N, M, smask);
-        h->wpriv_bytes = sizeof(double) * h->prm.wpriv_stride * (size_t)h->wpp_grid;
+        h->prm.wpriv_stride = b2_wpp_priv_doubles(N, M, smask);              // RTI launches keep their compact blocks (L2 footprint)
+        h->wpriv_stride_sqp = b2_wpp_priv_doubles(N, M, smask, true);
+        h->wpriv_bytes = sizeof(double) * h->wpriv_stride_sqp * (size_t)h->wpp_grid;
         if (h->wpriv_bytes) {
             if (cudaMalloc(&h->wpriv, h->wpriv_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(node-private rows, %zu B) failed", h->wpriv_bytes); }
             cudaMemset(h->wpriv, 0, h->wpriv_bytes);
@@ -719,7 +728,8 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
         p.NEXT = next;
         if (sqp) {
             const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);
-            h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem, st>>>(p);
+            p.wpriv_stride = h->wpriv_stride_sqp;
+            h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem_sqp, st>>>(p);
         } else if (h->wpp_fn_small && batch <= h->small_batch_max) {
             h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
         } else {

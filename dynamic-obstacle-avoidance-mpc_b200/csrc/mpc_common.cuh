@@ -45,8 +45,10 @@ struct B2Params {
     int32_t N, M, B, Bm;         // horizon, obstacles, batch in this launch, row stride (= max_batch)
     int32_t integrator, qp_iter_max, pred_corr, cond_pred_corr, itref_corr_max;
     int32_t nct;                 // padded constraints per node = 12 + 4M
-    int32_t nlp_iter_max;        // full-SQP mode: QP limit and the four residual tolerances
+    int32_t nlp_iter_max;        // full-SQP mode: QP limit, the four residual tolerances, line search
+    int32_t nlp_globalization;   // 0 FIXED_STEP, 1 MERIT_BACKTRACKING
     double nlp_tol[4];
+    double ls_alpha_min, ls_alpha_red;
     int32_t slots_per_stage;
     double dt, dt2h;             // h, h*h/2
     double Hd[7], Hde[7];        // Hessian diagonals (stage / terminal), LM included

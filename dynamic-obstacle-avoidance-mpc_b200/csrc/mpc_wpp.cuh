@@ -40,8 +40,10 @@ __constant__ unsigned char B2_BATAB[5][7] = {
 enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; dd = dlam (or dt*dlam of the predictor), dt = dt
        PF_B, PF_G, PF_RG, PF_XU,                            // 5, 7, 7, 6 rows
        PF_CX, PF_CY, PF_LG, PF_UG, PF_ZLQ, PF_ZZLQ, PF_SLI, PF_SUI, PF_SL, PF_SU,
-       PF_LRGSL, PF_LRGSU, PF_DSL, PF_DSU, PF_DLI, PF_DUI, PF_COUNT };
-#define B2_WPP_ALL_SHARED 0x1ffffffu
+       PF_LRGSL, PF_LRGSU, PF_DSL, PF_DSU, PF_DLI, PF_DUI,
+       PF_WPI, PF_WLAM,                                      // merit-function weights of the SQP line search (SQP kernels only)
+       PF_COUNT };
+#define B2_WPP_ALL_SHARED 0x7ffffffu
 // Placement used by default: EVERY node-private field in global memory.  Measured on B200 (N=20, M=5, 4096 problems,
 // profiles/experiments/r01_hybrid_layout.md): all global, 12 CTAs/SM 11.6 ms; lam,t shared, 7 CTAs/SM 13.1 ms;
 // lam,t,1/t,dlam shared, 5 CTAs/SM 14.3 ms; all shared, 4 CTAs/SM 12.7 ms.
@@ -55,11 +57,12 @@ struct WOff {
     int pf[PF_COUNT];                                                           // row of each private field in ITS space
     int total;                                                                  // shared-memory rows (incl. private fields placed there)
     int gtotal;                                                                 // global-memory rows
-    __host__ __device__ static int pf_rows(int f, int M)
+    __host__ __device__ static int pf_rows(int f, int M, bool sqp)
     {
+        if (f >= PF_WPI) return !sqp ? 0 : f == PF_WPI ? 5 : 12 + 4 * M;
         return f <= PF_DT ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
     }
-    __host__ __device__ WOff(int M, unsigned smask)
+    __host__ __device__ WOff(int M, unsigned smask, bool sqp)
     {
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
@@ -67,8 +70,8 @@ struct WOff {
         v = o; o += 7; pi = o; o += 5;
         int g = 0;
         for (int f = 0; f < PF_COUNT; f++) {
-            if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M); }
-            else { pf[f] = g; g += pf_rows(f, M); }
+            if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); }
+            else { pf[f] = g; g += pf_rows(f, M, sqp); }
         }
         total = o;
         gtotal = g;
@@ -78,13 +81,13 @@ struct WOff {
 __host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd shared-memory row stride
 __host__ __device__ inline int b2_wpp_gstride(int N) { return N + 1; }               // global rows packed (footprint over sector alignment)
 #define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
-__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned smask)
+__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned smask, bool sqp = false)
 {
-    return sizeof(double) * ((size_t)WOff(M, smask).total * b2_wpp_stride(N) + B2_WPP_SCRATCH);
+    return sizeof(double) * ((size_t)WOff(M, smask, sqp).total * b2_wpp_stride(N) + B2_WPP_SCRATCH);
 }
-__host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned smask)    // per resident CTA
+__host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned smask, bool sqp = false)    // per resident CTA
 {
-    return (size_t)WOff(M, smask).gtotal * b2_wpp_gstride(N);
+    return (size_t)WOff(M, smask, sqp).gtotal * b2_wpp_gstride(N);
 }
 
 // y ~ 1/x (a few ulp) -> one Newton step: the result is within an ulp of the correctly rounded reciprocal
@@ -139,7 +142,7 @@ struct WppSolver {
     __device__ WppSolver(const B2Params& p_, int b_, double* sm_, double* gm_)
         : p(p_), b(b_), lane(threadIdx.x & 31), N(NT > 0 ? NT : p_.N), NS(b2_wpp_stride(NT > 0 ? NT : p_.N)),
           GS(b2_wpp_gstride(NT > 0 ? NT : p_.N)), M(MT > 0 ? MT : p_.M),
-          nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), gm(gm_), o(MT > 0 ? MT : p_.M, SMASK), Bm((size_t)p_.Bm),
+          nct(12 + 4 * (MT > 0 ? MT : p_.M)), sm(sm_), gm(gm_), o(MT > 0 ? MT : p_.M, SMASK, SQP), Bm((size_t)p_.Bm),
           k(threadIdx.x & 31),
           o_lb(0), o_lg(6), o_ub(6 + (MT > 0 ? MT : p_.M)), o_ug(12 + (MT > 0 ? MT : p_.M)),
           o_ls(12 + 2 * (MT > 0 ? MT : p_.M)), o_us(12 + 3 * (MT > 0 ? MT : p_.M))
@@ -968,6 +971,91 @@ struct WppSolver {
         res[0] = b2_warp_max_nonneg(n0); res[1] = b2_warp_max_nonneg(n1); res[2] = b2_warp_max_nonneg(n2); res[3] = b2_warp_max_nonneg(n3);
     }
 
+    // ---- full-SQP mode, globalization MERIT_BACKTRACKING (acados ocp_nlp_line_search): l1 merit function
+    //   cost + sum w_pi |dynamics gap| + sum w_lam max(0, violation)   (slacks and their penalties included)
+    // at the trial point iterate + al * QP step; node-parallel, one model evaluation per node.  The x0 embedding
+    // (node 0, eliminated from the QP) is always taken in full.
+    __device__ double merit(double al)
+    {
+        double m = 0.0;
+        for (k = lane; k <= N; k += 32) {
+            double xk[5], uk[2] = {0.0, 0.0};
+            const double ax = k == 0 ? 1.0 : al;
+#pragma unroll
+            for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b] + ax * S(o.v + 2 + i, k);
+            const double* yr = p.YREF + ((size_t)k * 6) * Bm + b;
+            const double sc = scal(k);
+            const double* Wc = k < N ? p.Wg : p.Wge;
+            double cst = Wc[2] * (xk[0] - yr[0 * Bm]) * (xk[0] - yr[0 * Bm]) + Wc[3] * (xk[1] - yr[1 * Bm]) * (xk[1] - yr[1 * Bm])
+                       + Wc[5] * (xk[3] - yr[2 * Bm]) * (xk[3] - yr[2 * Bm]) + Wc[6] * (xk[4] - yr[3 * Bm]) * (xk[4] - yr[3 * Bm]);
+            double mk = 0.0;
+            if (k < N) {
+                uk[0] = p.U[((size_t)k * 2 + 0) * Bm + b] + al * S(o.v + 0, k);
+                uk[1] = p.U[((size_t)k * 2 + 1) * Bm + b] + al * S(o.v + 1, k);
+                cst += Wc[0] * (uk[0] - yr[4 * Bm]) * (uk[0] - yr[4 * Bm]) + Wc[1] * (uk[1] - yr[5 * Bm]) * (uk[1] - yr[5 * Bm]);
+                double xn[5], sv[10];
+                if (p.integrator == 1) model_rk4_step(xk, uk, p.dt, xn, sv);
+                else model_gl4_step(xk, uk, p.dt, xn, sv);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const double xn1 = p.X[((size_t)(k + 1) * 5 + i) * Bm + b] + al * S(o.v + 2 + i, k + 1);
+                    mk += Q<PF_WPI>(i) * fabs(xn[i] - xn1);
+                }
+            }
+            mk += 0.5 * cst;
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                const double val = s < 2 ? uk[s] : xk[b2_slot2v(s) - 2];
+                const double lo = s < 2 ? p.lbu[s] : p.lbx[s - 2], hi = s < 2 ? p.ubu[s] : p.ubx[s - 2];
+                mk += Q<PF_WLAM>(o_lb + s) * fmax(0.0, lo - val) + Q<PF_WLAM>(o_ub + s) * fmax(0.0, val - hi);
+            }
+#pragma unroll JU
+            for (int j = 0; j < M; j++) {
+                double hval, cx, cy;
+                model_con_h(xk, p.P[((size_t)k * 2 * M + 2 * j) * Bm + b], p.P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b], p.r2, &hval, &cx, &cy);
+                const double s_l = p.SL[((size_t)k * M + j) * Bm + b] + al * Q<PF_SL>(j);
+                const double s_u = p.SU[((size_t)k * M + j) * Bm + b] + al * Q<PF_SU>(j);
+                const double zl_in = p.ZL[((size_t)k * M + j) * Bm + b], Zl_in = p.ZZL[((size_t)k * M + j) * Bm + b];
+                mk += Q<PF_WLAM>(o_lg + j) * fmax(0.0, p.lh - hval - s_l) + Q<PF_WLAM>(o_ug + j) * fmax(0.0, hval - p.uh - s_u);
+                mk += sc * (zl_in * s_l + 0.5 * Zl_in * s_l * s_l + p.zu * s_u + 0.5 * p.Zu * s_u * s_u);
+                mk += Q<PF_WLAM>(o_ls + j) * fmax(0.0, -s_l) + Q<PF_WLAM>(o_us + j) * fmax(0.0, -s_u);
+            }
+            m += mk;
+        }
+        return b2_warp_sum(m);
+    }
+
+    // weights |multipliers| of the QP at the first SQP iteration, max(|mult|, (w + |mult|)/2) afterwards; then
+    // alpha = 1, 0.7, 0.49, ... until the merit function decreases (alpha_min is accepted untested)
+    __device__ double line_search(bool first)
+    {
+        for (k = lane; k <= N; k += 32) {
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const double a = fabs(S(o.pi + i, k));
+                    Q<PF_WPI>(i) = first ? a : fmax(a, 0.5 * (Q<PF_WPI>(i) + a));
+                }
+            }
+            for (int i = 0; i < nct; i++) {
+                const double a = fabs(Q<PF_LAM>(i));
+                Q<PF_WLAM>(i) = first ? a : fmax(a, 0.5 * (Q<PF_WLAM>(i) + a));
+            }
+        }
+        __syncwarp();
+        const double m0 = merit(0.0);
+        double al = 1.0;
+        for (;;) {
+            if (al <= p.ls_alpha_min) break;
+            const double m1 = merit(al);
+            if (m1 < m0) break;
+            al *= p.ls_alpha_red;
+            if (al < p.ls_alpha_min) al = p.ls_alpha_min;
+        }
+        return al;
+    }
+
     // ---- the whole call: one RTI iteration (SQP = false, the reference: nlp_solver_type 'SQP_RTI',
     // robot_ocp_problem.py:130), or acados' full `SQP` loop with FIXED_STEP globalisation (SQP = true:
     // [linearise -> NLP residuals -> convergence test -> QP -> full step] up to nlp_iter_max QPs, the iterate
@@ -976,7 +1064,7 @@ struct WppSolver {
     __device__ void run()
     {
         int sqp_it = 0, qp_total = 0, status = 0, qs = 0, n_itref = 0;
-        double nres[4] = {0.0, 0.0, 0.0, 0.0};
+        double nres[4] = {0.0, 0.0, 0.0, 0.0}, last_al = 1.0;
         for (;;) {
         prepare_and_init();
         if (SQP) {
@@ -1027,6 +1115,37 @@ struct WppSolver {
         else qs = 0;
         status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate untouched
         qp_total += kk;
+        double al = 1.0;
+        if (SQP && p.nlp_globalization && status == 0) al = line_search(sqp_it == 0);
+        last_al = al;
+        if (SQP && al < 1.0) {
+            // damped step: primal and dual variables move by al (the x0 embedding in full)
+            for (k = lane; k <= N; k += 32) {
+                const double ax = k == 0 ? 1.0 : al;
+#pragma unroll
+                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += ax * S(o.v + 2 + i, k);
+                if (k < N) {
+                    p.U[((size_t)k * 2 + 0) * Bm + b] += al * S(o.v + 0, k);
+                    p.U[((size_t)k * 2 + 1) * Bm + b] += al * S(o.v + 1, k);
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        double* d = p.PI + ((size_t)k * 5 + i) * Bm + b;
+                        *d += al * (S(o.pi + i, k) - *d);
+                    }
+                }
+#pragma unroll JU
+                for (int j = 0; j < M; j++) {
+                    p.SL[((size_t)k * M + j) * Bm + b] += al * Q<PF_SL>(j);
+                    p.SU[((size_t)k * M + j) * Bm + b] += al * Q<PF_SU>(j);
+                }
+                for (int i = 0; i < nct; i++) {
+                    double* dl = p.LAM + ((size_t)k * nct + i) * Bm + b;
+                    double* dt_ = p.T + ((size_t)k * nct + i) * Bm + b;
+                    *dl += al * (Q<PF_LAM>(i) - *dl);
+                    *dt_ += al * (Q<PF_T>(i) - *dt_);
+                }
+            }
+        } else
         for (k = lane; k <= N; k += 32) {
             if (status == 0) {
 #pragma unroll
@@ -1059,6 +1178,7 @@ struct WppSolver {
             p.STATS[0 * Bm + b] = nrm[0]; p.STATS[1 * Bm + b] = nrm[1]; p.STATS[2 * Bm + b] = nrm[2]; p.STATS[3 * Bm + b] = nrm[3];
             p.STATS[4 * Bm + b] = mu; p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
             if (SQP) {
+                p.STATS[7 * Bm + b] = last_al;
                 p.SQP_ITER[b] = sqp_it;
                 p.NLP_RES[0 * Bm + b] = nres[0]; p.NLP_RES[1 * Bm + b] = nres[1]; p.NLP_RES[2 * Bm + b] = nres[2]; p.NLP_RES[3 * Bm + b] = nres[3];
             }

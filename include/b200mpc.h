@@ -65,6 +65,11 @@ typedef struct b2mpc_config {
     int32_t nlp_solver;
     int32_t nlp_iter_max;    /* solver_options.nlp_solver_max_iter (acados default 100); SQP only */
     double nlp_tol[4];       /* nlp_solver_tol_stat / _eq / _ineq / _comp (acados default 1e-6 each); SQP only */
+    int32_t nlp_globalization; /* solver_options.globalization: 0 = 'FIXED_STEP' (full steps, acados default),
+                                  1 = 'MERIT_BACKTRACKING' (l1 merit function, alpha <- alpha * ls_alpha_reduction while it
+                                  does not decrease, primal and dual variables move by alpha); SQP only */
+    int32_t reserved2;
+    double ls_alpha_min, ls_alpha_reduction;   /* alpha_min (0.05), alpha_reduction (0.7) */
 } b2mpc_config;
 
 /* fields of b2mpc_set / b2mpc_get; len = doubles per problem */
@@ -81,7 +86,7 @@ enum {
     B2MPC_PI = 9,     /* [N*5]          get(i,'pi')  (output; SQP: in/out, reset() zeroes)   */
     B2MPC_LAM = 10,   /* [(N+1)*(12+4M)] get(i,'lam') padded [lb6 lg ub6 ug ls us] (same)    */
     B2MPC_T = 11,     /* [(N+1)*(12+4M)] get(i,'t')   (same)                                 */
-    B2MPC_STATS = 12, /* [8] res_g,res_b,res_d,res_m,mu,alpha,n_itref,0 at exit (output)     */
+    B2MPC_STATS = 12, /* [8] res_g,res_b,res_d,res_m,mu,alpha,n_itref,0 (SQP: last line-search step) */
     B2MPC_GOAL = 13,  /* [2]            sub-goal used by b2mpc_prepare_slack / closed loop   */
     B2MPC_OBST = 14,  /* [M*4]          obstacle states (x,y,vx,vy), visualization.py:10-18  */
     B2MPC_MARGIN = 15, /* [2]           closed loop: min_margin_traj, distance_to_goal (:222-228,:246) */

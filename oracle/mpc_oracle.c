@@ -1075,25 +1075,119 @@ void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p
     res[0] = r0; res[1] = r1; res[2] = r2; res[3] = r3;
 }
 
-/* SQP with full steps: returns acados status 0 (converged), 2 (max_iter), 4 (QP failure).
+/* merit function of acados' MERIT_BACKTRACKING line search (ocp_nlp_evaluate_merit_fun): cost + sum w_pi |dynamics gap|
+ * + sum w_lam max(0, constraint violation), slack variables and their penalties included.  x[0] is the embedded x0bar. */
+static double sqp_merit(const orc_config *c, const double *p, const double *yref, const double *zl, const double *Zl,
+                        const double *x, const double *u, const double *sl, const double *su,
+                        const double *wpi, const double *wlam)
+{
+    const int N = c->N, M = c->M, nct = 12 + 4 * M;
+    const double dt = c->tf / N;
+    static const int idxbx[4] = {0, 1, 3, 4};
+    double m = 0.0;
+    for (int k = 0; k <= N; k++) {
+        const double *xk = x + k * NX, *uk = u + k * NU, *yr = yref + k * ORC_NY;
+        const double *wk = wlam + (size_t)k * nct;
+        const double scal = k < N ? dt : 1.0;
+        double mk = 0.0;
+        if (k < N) {
+            double xn[5];
+            if (c->integrator == 1) orc_rk4_step(xk, uk, dt, xn, NULL, NULL);
+            else orc_gl4_step(xk, uk, dt, xn, NULL, NULL);
+            for (int r = 0; r < NX; r++) mk += wpi[k * NX + r] * fabs(xn[r] - x[(k + 1) * NX + r]);
+            double cst = 0.0;
+            for (int j = 0; j < NU; j++) cst += c->W[4 + j] * (uk[j] - yr[4 + j]) * (uk[j] - yr[4 + j]);
+            for (int j = 0; j < 4; j++) cst += c->W[j] * (xk[idxbx[j]] - yr[j]) * (xk[idxbx[j]] - yr[j]);
+            mk += 0.5 * scal * cst;
+        } else {
+            double cst = 0.0;
+            for (int j = 0; j < 4; j++) cst += c->We[j] * (xk[idxbx[j]] - yr[j]) * (xk[idxbx[j]] - yr[j]);
+            mk += 0.5 * cst;
+        }
+        for (int s = 0; s < 6; s++) {
+            const int on = s < 2 ? (k < N) : (k > 0 && k < N);
+            if (!on) continue;
+            const double val = s < 2 ? uk[s] : xk[idxbx[s - 2]];
+            const double lo = s < 2 ? c->lbu[s] : c->lbx[s - 2], hi = s < 2 ? c->ubu[s] : c->ubx[s - 2];
+            mk += wk[s] * fmax(0.0, lo - val) + wk[6 + M + s] * fmax(0.0, val - hi);
+        }
+        double hh[MM], cx[MM], cy[MM];
+        orc_con_h(xk, p + (size_t)k * 2 * M, M, c->r2, hh, cx, cy);
+        for (int j = 0; j < M; j++) {
+            const double s_l = c->soft ? sl[k * M + j] : 0.0, s_u = c->soft ? su[k * M + j] : 0.0;
+            mk += wk[6 + j] * fmax(0.0, c->lh - hh[j] - s_l) + wk[12 + M + j] * fmax(0.0, hh[j] - c->uh - s_u);
+            if (c->soft) {
+                mk += scal * (zl[k * M + j] * s_l + 0.5 * Zl[k * M + j] * s_l * s_l + c->zu * s_u + 0.5 * c->Zu * s_u * s_u);
+                mk += wk[12 + 2 * M + j] * fmax(0.0, -s_l) + wk[12 + 3 * M + j] * fmax(0.0, -s_u);
+            }
+        }
+        m += mk;
+    }
+    return m;
+}
+
+/* SQP: returns acados status 0 (converged), 2 (max_iter), 4 (QP failure).
+ * globalization 0 = FIXED_STEP (full steps, acados' default), 1 = MERIT_BACKTRACKING (alpha <- 0.7 alpha while the
+ * merit function does not decrease, alpha_min 0.05; weights |multipliers| at the first iteration, then
+ * max(|mult|, (w + |mult|)/2); primal AND dual variables move by alpha; the x0 embedding is always taken in full,
+ * x0 being eliminated from the QP).
  * pi/lam/t are IN/OUT (multipliers of the previous call or zeros); *sqp_iter = QPs solved, *qp_iter = their
  * interior-point iterations in total, res[4] = NLP residuals at exit. */
-int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4],
+int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int globalization,
                   const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                   double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                   int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats)
 {
+    const int N = c->N, M = c->M, nct = 12 + 4 * M;
+    const size_t nxs = (size_t)(N + 1) * NX, nus = (size_t)N * NU, nss = (size_t)(N + 1) * M, nls = (size_t)(N + 1) * nct;
     int it = 0, qtot = 0, status;
     double r[4], st8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double *w = NULL;
+    if (globalization) w = (double *)calloc((size_t)(N + 1) * NV + 2 * nss + (size_t)N * NX * 2 + 3 * nls + nxs + nus + 2 * nss, sizeof(double));
+    double *v = w, *dsl = v ? v + (size_t)(N + 1) * NV : NULL, *dsu = v ? dsl + nss : NULL, *pq = v ? dsu + nss : NULL;
+    double *wpi = v ? pq + (size_t)N * NX : NULL, *lq = v ? wpi + (size_t)N * NX : NULL, *tq = v ? lq + nls : NULL, *wlam = v ? tq + nls : NULL;
+    double *xt = v ? wlam + nls : NULL, *ut = v ? xt + nxs : NULL, *slt = v ? ut + nus : NULL, *sut = v ? slt + nss : NULL;
     for (;; it++) {
         orc_nlp_residuals(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, r);
         if (r[0] < tol[0] && r[1] < tol[1] && r[2] < tol[2] && r[3] < tol[3]) { status = 0; break; }
         if (it >= max_iter) { status = 2; break; }
         int32_t qi = 0, qs = 0;
-        const int s = orc_rti_solve(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, &qi, &qs, st8);
+        if (!globalization) {
+            const int s = orc_rti_solve(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, &qi, &qs, st8);
+            qtot += qi;
+            if (s != 0) { status = s; it++; break; }
+            continue;
+        }
+        orc_qp_solve_export(c, x0bar, p, yref, zl, Zl, x, u, sl, su, v, dsl, dsu, pq, lq, tq, &qi, &qs, st8);
         qtot += qi;
-        if (s != 0) { status = s; it++; break; }
+        if (qs != 0 && qs != 1) { status = 4; it++; memcpy(lam, lq, nls * sizeof(double)); memcpy(t, tq, nls * sizeof(double)); break; }
+        for (int i = 0; i < NX; i++) x[i] += v[2 + i];                       /* embedding: x_0 <- x0bar */
+        for (size_t i = 0; i < (size_t)N * NX; i++) { const double a = fabs(pq[i]); wpi[i] = it == 0 ? a : fmax(a, 0.5 * (wpi[i] + a)); }
+        for (size_t i = 0; i < nls; i++) { const double a = fabs(lq[i]); wlam[i] = it == 0 ? a : fmax(a, 0.5 * (wlam[i] + a)); }
+        const double m0 = sqp_merit(c, p, yref, zl, Zl, x, u, sl, su, wpi, wlam);
+        double alpha = 1.0;
+        for (;;) {
+            for (int i = 0; i < NX; i++) xt[i] = x[i];
+            for (int k = 1; k <= N; k++) for (int i = 0; i < NX; i++) xt[k * NX + i] = x[k * NX + i] + alpha * v[k * NV + 2 + i];
+            for (int k = 0; k < N; k++) for (int i = 0; i < NU; i++) ut[k * NU + i] = u[k * NU + i] + alpha * v[k * NV + i];
+            for (size_t i = 0; i < nss; i++) { slt[i] = sl[i] + alpha * dsl[i]; sut[i] = su[i] + alpha * dsu[i]; }
+            if (alpha <= 0.05) break;                                        /* alpha_min: accepted without a test */
+            const double m1 = sqp_merit(c, p, yref, zl, Zl, xt, ut, slt, sut, wpi, wlam);
+            if (m1 < m0) break;
+            alpha *= 0.7;
+            if (alpha < 0.05) alpha = 0.05;
+        }
+        memcpy(x, xt, nxs * sizeof(double)); memcpy(u, ut, nus * sizeof(double));
+        memcpy(sl, slt, nss * sizeof(double)); memcpy(su, sut, nss * sizeof(double));
+        if (alpha == 1.0) {
+            memcpy(pi, pq, (size_t)N * NX * sizeof(double)); memcpy(lam, lq, nls * sizeof(double)); memcpy(t, tq, nls * sizeof(double));
+        } else {
+            for (size_t i = 0; i < (size_t)N * NX; i++) pi[i] += alpha * (pq[i] - pi[i]);
+            for (size_t i = 0; i < nls; i++) { lam[i] += alpha * (lq[i] - lam[i]); t[i] += alpha * (tq[i] - t[i]); }
+        }
+        st8[7] = alpha;
     }
+    free(w);
     if (sqp_iter) *sqp_iter = it;
     if (qp_iter) *qp_iter = qtot;
     if (res) memcpy(res, r, sizeof(r));
@@ -1102,7 +1196,7 @@ int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4],
 }
 
 typedef struct {
-    const orc_config *c; int64_t B; atomic_llong next; int max_iter; const double *tol;
+    const orc_config *c; int64_t B; atomic_llong next; int max_iter; const double *tol; int glob;
     const double *x0bar, *p, *yref, *zl, *Zl;
     double *x, *u, *sl, *su, *pi, *lam, *t; int32_t *status, *sqp_iter, *qp_iter; double *res;
 } sqp_job;
@@ -1118,7 +1212,7 @@ static void *sqp_worker(void *arg)
         long long b = atomic_fetch_add(&j->next, 1);
         if (b >= j->B) break;
         int32_t it = 0, qi = 0;
-        int s = orc_sqp_solve(c, j->max_iter, j->tol, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
+        int s = orc_sqp_solve(c, j->max_iter, j->tol, j->glob, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
                               j->zl + b * nss, j->Zl + b * nss, j->x + b * nxs, j->u + b * nus, j->sl + b * nss, j->su + b * nss,
                               j->pi + b * (size_t)N * NX, j->lam + b * nls, j->t + b * nls, &it, &qi, j->res + b * 4, NULL);
         j->status[b] = s; j->sqp_iter[b] = it; j->qp_iter[b] = qi;
@@ -1126,12 +1220,12 @@ static void *sqp_worker(void *arg)
     return NULL;
 }
 
-void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4],
+void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4], int globalization,
                          const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                          double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                          int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res)
 {
-    sqp_job j = {c, B, 0, max_iter, tol, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, status, sqp_iter, qp_iter, res};
+    sqp_job j = {c, B, 0, max_iter, tol, globalization, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, status, sqp_iter, qp_iter, res};
     atomic_init(&j.next, 0);
     if (nthreads <= 1) { sqp_worker(&j); return; }
     if (nthreads > 256) nthreads = 256;

@@ -101,13 +101,14 @@ void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p
                        const double *yref, const double *zl, const double *Zl,
                        const double *x, const double *u, const double *sl, const double *su,
                        const double *pi, const double *lam, const double *t, double res[4]);
-/* acados `SQP` with FIXED_STEP: [residuals -> test against tol[4] -> QP -> full step] up to max_iter QPs.
+/* acados `SQP`: [residuals -> test against tol[4] -> QP -> step] up to max_iter QPs; globalization 0 = FIXED_STEP
+ * (full steps), 1 = MERIT_BACKTRACKING (alpha *= 0.7 while the l1 merit function does not decrease, alpha_min 0.05).
  * pi/lam/t in/out (previous multipliers or zeros).  Returns 0 converged, 2 max_iter, 4 QP failure. */
-int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4],
+int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int globalization,
                   const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                   double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                   int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats);
-void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4],
+void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4], int globalization,
                          const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                          double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                          int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res);

@@ -51,20 +51,25 @@ def test_one_sqp_iteration_is_the_rti_step(torch_cuda, kernel):
     assert np.array_equal(sqp["status"] == 4, rti["status"] == 4) and set(np.unique(sqp["status"])) <= {2, 4}
 
 
-@pytest.mark.parametrize("N,M,tf,B,kernel", [(20, 5, 2.0, 192, 0), (20, 5, 2.0, 96, 3), (12, 3, 1.2, 100, 0)])
-def test_sqp_matches_oracle(torch_cuda, oracle, N, M, tf, B, kernel):
+# nlp_tol: the acados default 1e-6 leaves the iterate determined to ~tol / curvature (the heading has no cost: its
+# curvature is the Levenberg-Marquardt term dt*lm = 0.2) = 5e-6, so two correct runs may differ by that much: bar 1e-5.
+# With tolerances of 1e-8 (and the QP's own stationarity tolerance below that) the north_star bar of 1e-6 applies.
+@pytest.mark.parametrize("N,M,tf,B,kernel,nlp_tol,bar", [(20, 5, 2.0, 192, 0, 1e-6, 1e-5), (20, 5, 2.0, 128, 0, 1e-8, 1e-6),
+                                                          (20, 5, 2.0, 96, 3, 1e-8, 1e-6), (12, 3, 1.2, 100, 0, 1e-6, 1e-5)])
+def test_sqp_matches_oracle(torch_cuda, oracle, N, M, tf, B, kernel, nlp_tol, bar):
     from b200mpc import BatchedMpcSolver
     dims = world.MpcDims(N, M, tf)
     sc = world.random_scenarios(B, dims, seed=14, moving_start=True)
-    max_iter = 250
-    s = BatchedMpcSolver(N, M, tf, max_batch=B, kernel=kernel, nlp_solver=1, nlp_iter_max=max_iter)
+    max_iter = 250 if nlp_tol > 1e-7 else 400
+    over = {} if nlp_tol > 1e-7 else dict(res_g_max=1e-9)
+    s = BatchedMpcSolver(N, M, tf, max_batch=B, kernel=kernel, nlp_solver=1, nlp_iter_max=max_iter, nlp_tol=(nlp_tol,) * 4, **over)
     _load(torch_cuda, s, sc, B)
     s.solve(B)                                            # cfg.nlp_solver = 1: solve() IS the SQP loop
     out = _read(s, B)
-    cfg = oracle.default_config(N, M, tf)
+    cfg = oracle.default_config(N, M, tf, **over)
     ref = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
     r = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], ref["x"], ref["u"], ref["sl"], ref["su"],
-                               max_iter=max_iter, nthreads=8)
+                               max_iter=max_iter, tol=(nlp_tol,) * 4, nthreads=8)
     conv = (r["status"] == 0) & (out["status"] == 0)
     assert conv.mean() > 0.5
     assert np.mean(out["status"] == r["status"]) >= 0.97
@@ -75,9 +80,9 @@ def test_sqp_matches_oracle(torch_cuda, oracle, N, M, tf, B, kernel):
     same = conv & (out["sqp_iter"] == r["sqp_iter"])
     for k in ("u", "x"):
         e = np.abs(out[k] - ref[k]).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(ref[k]).reshape(B, -1).max(1))
-        assert e[same].max() < 1e-6, (k, e[same].max())
-        assert e[conv].max() < 1e-4, (k, e[conv].max())      # one iteration more or less at tolerance 1e-6
-    assert (out["nlp_res"][out["status"] == 0] < 1e-6).all()
+        assert e[same].max() < bar, (k, e[same].max())
+        assert e[conv].max() < 100 * bar, (k, e[conv].max())   # one iteration more or less at the tolerance
+    assert (out["nlp_res"][out["status"] == 0] < nlp_tol).all()
     assert (out["sqp_iter"][out["status"] == 2] == max_iter).all()
     # the reported residuals are the NLP's: recompute them with the oracle from what the GPU returned
     for b in np.nonzero(out["status"] == 0)[0][:8]:
@@ -113,3 +118,37 @@ def test_sqp_options_and_errors(torch_cuda):
     with pytest.raises(capi.B2mpcError):
         t.solve_sqp(8)
     t.close()
+
+
+def test_merit_backtracking_matches_oracle(torch_cuda, oracle):
+    """globalization = MERIT_BACKTRACKING with a small Levenberg-Marquardt weight (where the line search matters):
+    same converged set and iteration counts as the oracle up to the merit comparisons that rounding decides
+    (the merit function is a sum over all nodes in a different order on the two sides), same solutions."""
+    from b200mpc import BatchedMpcSolver
+    B, lm, max_iter = 192, 0.05, 100
+    sc = world.random_scenarios(B, DIMS, seed=14, moving_start=True)
+    s = BatchedMpcSolver(20, 5, 2.0, max_batch=B, lm=lm, nlp_solver=1, nlp_iter_max=max_iter, nlp_globalization=1)
+    _load(torch_cuda, s, sc, B)
+    s.solve(B)
+    out = _read(s, B)
+    s.close()
+    cfg = oracle.default_config(20, 5, 2.0, lm=lm)
+    ref = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    r = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], ref["x"], ref["u"], ref["sl"], ref["su"],
+                               max_iter=max_iter, nthreads=8, globalization=1)
+    # and the same problems WITHOUT the line search, on the GPU
+    s0 = BatchedMpcSolver(20, 5, 2.0, max_batch=B, lm=lm, nlp_solver=1, nlp_iter_max=max_iter)
+    _load(torch_cuda, s0, sc, B)
+    s0.solve(B)
+    st0 = s0.get_int("status", B).cpu().numpy()
+    s0.close()
+    assert np.mean(out["status"] == 0) >= np.mean(st0 == 0) + 0.1          # the line search rescues oscillating problems
+    assert abs(np.mean(out["status"] == 0) - np.mean(r["status"] == 0)) <= 0.08
+    assert np.mean(out["status"] == r["status"]) >= 0.85
+    conv = (r["status"] == 0) & (out["status"] == 0)
+    d = np.abs(out["sqp_iter"] - r["sqp_iter"])
+    assert np.mean(d[conv] == 0) >= 0.7, np.mean(d[conv] == 0)
+    same = conv & (d == 0)
+    e = np.abs(out["u"] - ref["u"]).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(ref["u"]).reshape(B, -1).max(1))
+    assert np.median(e[same]) < 1e-9 and np.mean(e[same] < 1e-5) >= 0.97
+    assert (out["nlp_res"][out["status"] == 0] < 1e-6).all()

@@ -133,3 +133,43 @@ def test_looser_tolerance_needs_fewer_iterations(oracle):
                                    max_iter=300, tol=(tol,) * 4, nthreads=8)
         its.append(r["sqp_iter"])
     assert (its[0] <= its[1]).all() and its[0].mean() < its[1].mean()
+
+
+def test_merit_backtracking_helps_where_full_steps_oscillate(oracle):
+    """globalization = MERIT_BACKTRACKING: with the reference's lm = 2 the Levenberg-Marquardt term already damps the
+    steps (the line search changes little); with a small lm full Gauss-Newton steps oscillate and the line search
+    rescues a good part of the problems."""
+    B = 96
+    sc = _scen(B, seed=1)
+    conv = {}
+    for lm, mi in ((2.0, 300), (0.05, 100)):
+        cfg = oracle.default_config(DIMS.N, DIMS.M, DIMS.tf, lm=lm)
+        for g in (0, 1):
+            w = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+            r = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], w["x"], w["u"], w["sl"], w["su"],
+                                       max_iter=mi, nthreads=8, globalization=g)
+            conv[(lm, g)] = np.mean(r["status"] == 0)
+            assert (r["res"][r["status"] == 0] < 1e-6).all()
+    assert abs(conv[(2.0, 1)] - conv[(2.0, 0)]) <= 0.05
+    assert conv[(0.05, 1)] >= conv[(0.05, 0)] + 0.1, conv
+
+
+def test_full_line_search_steps_equal_fixed_steps(oracle):
+    """one SQP iteration from the cold iterate with an accepted alpha = 1 is bit-identical to the FIXED_STEP iteration"""
+    B = 32
+    sc = _scen(B, seed=2)
+    cfg = oracle.default_config(DIMS.N, DIMS.M, DIMS.tf)
+    a = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    ra = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], a["x"], a["u"], a["sl"], a["su"], max_iter=1)
+    c = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    rc = oracle.sqp_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], c["x"], c["u"], c["sl"], c["su"], max_iter=1, globalization=1)
+    full = np.array([np.array_equal(a["u"][b], c["u"][b]) for b in range(B)])
+    assert full.mean() > 0.5                                  # most first steps are accepted in full ...
+    for b in np.nonzero(full)[0]:
+        assert np.array_equal(a["x"][b], c["x"][b]) and np.array_equal(ra["lam"][b], rc["lam"][b])
+    for b in np.nonzero(~full)[0]:                            # ... the others moved along the same direction, but less far
+        if ra["status"][b] == 4:
+            continue
+        d_full = a["u"][b] - sc["u"][b]; d_ls = c["u"][b] - sc["u"][b]
+        al = (d_full * d_ls).sum() / (d_full * d_full).sum()
+        assert 0.049 <= al < 1.0 and np.abs(d_ls - al * d_full).max() < 1e-9 * max(1.0, np.abs(d_full).max())
