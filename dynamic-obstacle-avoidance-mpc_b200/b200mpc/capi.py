@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("reg_prim", C.c_double), ("lam_min", C.c_double), ("t_min", C.c_double), ("tau_min", C.c_double), ("thr0", C.c_double),
         ("nlp_solver", C.c_int32), ("nlp_iter_max", C.c_int32), ("nlp_tol", C.c_double * 4),
         ("nlp_globalization", C.c_int32), ("reserved2", C.c_int32), ("ls_alpha_min", C.c_double), ("ls_alpha_reduction", C.c_double),
+        ("ls_eps", C.c_double),
     ]
 
 

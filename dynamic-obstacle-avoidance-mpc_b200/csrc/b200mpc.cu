@@ -88,6 +88,7 @@ extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst,
     for (int i = 0; i < 4; i++) c->nlp_tol[i] = 1e-6;
     c->nlp_globalization = 0;                                      // 'FIXED_STEP'
     c->ls_alpha_min = 0.05; c->ls_alpha_reduction = 0.7;           // acados line-search defaults
+    c->ls_eps = 0.0;                                               // relative slack of the merit decrease test (0 = the plain test)
 }
 
 static void fill_params(b2mpc* h)
@@ -101,7 +102,7 @@ static void fill_params(b2mpc* h)
     p.nct = h->nct;
     p.nlp_iter_max = c.nlp_iter_max; p.nlp_globalization = c.nlp_globalization;
     for (int i = 0; i < 4; i++) p.nlp_tol[i] = c.nlp_tol[i];
-    p.ls_alpha_min = c.ls_alpha_min; p.ls_alpha_red = c.ls_alpha_reduction;
+    p.ls_alpha_min = c.ls_alpha_min; p.ls_alpha_red = c.ls_alpha_reduction; p.ls_eps = c.ls_eps;
     p.slots_per_stage = B2Off(h->M).total;
     p.dt = c.tf / c.N; p.dt2h = 0.5 * p.dt * p.dt;
     const double lm_s = c.lm_scaled_by_dt ? p.dt * c.lm : c.lm;   // acados-version dependent

@@ -48,7 +48,7 @@ struct B2Params {
     int32_t nlp_iter_max;        // full-SQP mode: QP limit, the four residual tolerances, line search
     int32_t nlp_globalization;   // 0 FIXED_STEP, 1 MERIT_BACKTRACKING
     double nlp_tol[4];
-    double ls_alpha_min, ls_alpha_red;
+    double ls_alpha_min, ls_alpha_red, ls_eps;
     int32_t slots_per_stage;
     double dt, dt2h;             // h, h*h/2
     double Hd[7], Hde[7];        // Hessian diagonals (stage / terminal), LM included

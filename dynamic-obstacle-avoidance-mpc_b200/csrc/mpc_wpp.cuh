@@ -1027,7 +1027,8 @@ struct WppSolver {
     }
 
     // weights |multipliers| of the QP at the first SQP iteration, max(|mult|, (w + |mult|)/2) afterwards; then
-    // alpha = 1, 0.7, 0.49, ... until the merit function decreases (alpha_min is accepted untested)
+    // alpha = 1, 0.7, 0.49, ... until the merit function decreases (alpha_min is accepted untested; ls_eps: a few ulp of
+    // slack so that the rounding noise of the merit sum does not reject full steps near convergence)
     __device__ double line_search(bool first)
     {
         for (k = lane; k <= N; k += 32) {
@@ -1049,7 +1050,7 @@ struct WppSolver {
         for (;;) {
             if (al <= p.ls_alpha_min) break;
             const double m1 = merit(al);
-            if (m1 < m0) break;
+            if (m1 < m0 + p.ls_eps * fmax(1.0, fabs(m0))) break;
             al *= p.ls_alpha_red;
             if (al < p.ls_alpha_min) al = p.ls_alpha_min;
         }

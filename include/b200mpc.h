@@ -70,6 +70,9 @@ typedef struct b2mpc_config {
                                   does not decrease, primal and dual variables move by alpha); SQP only */
     int32_t reserved2;
     double ls_alpha_min, ls_alpha_reduction;   /* alpha_min (0.05), alpha_reduction (0.7) */
+    double ls_eps;           /* a step is accepted when merit(alpha) < merit(0) + ls_eps max(1, |merit(0)|); default 0 = the
+                                plain decrease test.  Near convergence the true decrease (~|step|^2) sinks below the rounding
+                                noise of the merit sum (slack penalties of 1e5..1e7): see DESIGN.md "line search" */
 } b2mpc_config;
 
 /* fields of b2mpc_set / b2mpc_get; len = doubles per problem */

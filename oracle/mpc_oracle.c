@@ -1128,20 +1128,23 @@ static double sqp_merit(const orc_config *c, const double *p, const double *yref
 
 /* SQP: returns acados status 0 (converged), 2 (max_iter), 4 (QP failure).
  * globalization 0 = FIXED_STEP (full steps, acados' default), 1 = MERIT_BACKTRACKING (alpha <- 0.7 alpha while the
- * merit function does not decrease, alpha_min 0.05; weights |multipliers| at the first iteration, then
+ * merit function does not decrease, alpha_min 0.05 -- ls[3] = {alpha_min, alpha_reduction, eps}, a step being accepted when
+ * merit(alpha) < merit(0) + eps max(1, |merit(0)|): eps = 0 is the plain test, a few ulp of slack keep the rounding noise
+ * of the merit sum from rejecting full steps near convergence; weights |multipliers| at the first iteration, then
  * max(|mult|, (w + |mult|)/2); primal AND dual variables move by alpha; the x0 embedding is always taken in full,
  * x0 being eliminated from the QP).
  * pi/lam/t are IN/OUT (multipliers of the previous call or zeros); *sqp_iter = QPs solved, *qp_iter = their
  * interior-point iterations in total, res[4] = NLP residuals at exit. */
-int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int globalization,
+int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int globalization, const double ls[3],
                   const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                   double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                   int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats)
 {
     const int N = c->N, M = c->M, nct = 12 + 4 * M;
     const size_t nxs = (size_t)(N + 1) * NX, nus = (size_t)N * NU, nss = (size_t)(N + 1) * M, nls = (size_t)(N + 1) * nct;
-    int it = 0, qtot = 0, status;
+    int it = 0, qtot = 0, status, n_maxed = 0;
     double r[4], st8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double ls_amin = ls ? ls[0] : 0.05, ls_red = ls ? ls[1] : 0.7, ls_eps = ls ? ls[2] : 0.0;
     double *w = NULL;
     if (globalization) w = (double *)calloc((size_t)(N + 1) * NV + 2 * nss + (size_t)N * NX * 2 + 3 * nls + nxs + nus + 2 * nss, sizeof(double));
     double *v = w, *dsl = v ? v + (size_t)(N + 1) * NV : NULL, *dsu = v ? dsl + nss : NULL, *pq = v ? dsu + nss : NULL;
@@ -1154,12 +1157,12 @@ int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int gl
         int32_t qi = 0, qs = 0;
         if (!globalization) {
             const int s = orc_rti_solve(c, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, &qi, &qs, st8);
-            qtot += qi;
+            qtot += qi; n_maxed += (qs == 1);
             if (s != 0) { status = s; it++; break; }
             continue;
         }
         orc_qp_solve_export(c, x0bar, p, yref, zl, Zl, x, u, sl, su, v, dsl, dsu, pq, lq, tq, &qi, &qs, st8);
-        qtot += qi;
+        qtot += qi; n_maxed += (qs == 1);
         if (qs != 0 && qs != 1) { status = 4; it++; memcpy(lam, lq, nls * sizeof(double)); memcpy(t, tq, nls * sizeof(double)); break; }
         for (int i = 0; i < NX; i++) x[i] += v[2 + i];                       /* embedding: x_0 <- x0bar */
         for (size_t i = 0; i < (size_t)N * NX; i++) { const double a = fabs(pq[i]); wpi[i] = it == 0 ? a : fmax(a, 0.5 * (wpi[i] + a)); }
@@ -1171,11 +1174,11 @@ int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int gl
             for (int k = 1; k <= N; k++) for (int i = 0; i < NX; i++) xt[k * NX + i] = x[k * NX + i] + alpha * v[k * NV + 2 + i];
             for (int k = 0; k < N; k++) for (int i = 0; i < NU; i++) ut[k * NU + i] = u[k * NU + i] + alpha * v[k * NV + i];
             for (size_t i = 0; i < nss; i++) { slt[i] = sl[i] + alpha * dsl[i]; sut[i] = su[i] + alpha * dsu[i]; }
-            if (alpha <= 0.05) break;                                        /* alpha_min: accepted without a test */
+            if (alpha <= ls_amin) break;                                     /* alpha_min: accepted without a test */
             const double m1 = sqp_merit(c, p, yref, zl, Zl, xt, ut, slt, sut, wpi, wlam);
-            if (m1 < m0) break;
-            alpha *= 0.7;
-            if (alpha < 0.05) alpha = 0.05;
+            if (m1 < m0 + ls_eps * fmax(1.0, fabs(m0))) break;
+            alpha *= ls_red;
+            if (alpha < ls_amin) alpha = ls_amin;
         }
         memcpy(x, xt, nxs * sizeof(double)); memcpy(u, ut, nus * sizeof(double));
         memcpy(sl, slt, nss * sizeof(double)); memcpy(su, sut, nss * sizeof(double));
@@ -1191,12 +1194,13 @@ int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int gl
     if (sqp_iter) *sqp_iter = it;
     if (qp_iter) *qp_iter = qtot;
     if (res) memcpy(res, r, sizeof(r));
+    st8[6] = n_maxed;                                /* QPs of this call that ran into qp_iter_max */
     if (stats) memcpy(stats, st8, sizeof(st8));
     return status;
 }
 
 typedef struct {
-    const orc_config *c; int64_t B; atomic_llong next; int max_iter; const double *tol; int glob;
+    const orc_config *c; int64_t B; atomic_llong next; int max_iter; const double *tol; int glob; const double *ls; int32_t *qp_maxed;
     const double *x0bar, *p, *yref, *zl, *Zl;
     double *x, *u, *sl, *su, *pi, *lam, *t; int32_t *status, *sqp_iter, *qp_iter; double *res;
 } sqp_job;
@@ -1212,20 +1216,23 @@ static void *sqp_worker(void *arg)
         long long b = atomic_fetch_add(&j->next, 1);
         if (b >= j->B) break;
         int32_t it = 0, qi = 0;
-        int s = orc_sqp_solve(c, j->max_iter, j->tol, j->glob, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
+        double st8[8];
+        int s = orc_sqp_solve(c, j->max_iter, j->tol, j->glob, j->ls, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
                               j->zl + b * nss, j->Zl + b * nss, j->x + b * nxs, j->u + b * nus, j->sl + b * nss, j->su + b * nss,
-                              j->pi + b * (size_t)N * NX, j->lam + b * nls, j->t + b * nls, &it, &qi, j->res + b * 4, NULL);
+                              j->pi + b * (size_t)N * NX, j->lam + b * nls, j->t + b * nls, &it, &qi, j->res + b * 4, st8);
         j->status[b] = s; j->sqp_iter[b] = it; j->qp_iter[b] = qi;
+        if (j->qp_maxed) j->qp_maxed[b] = (int32_t)st8[6];
     }
     return NULL;
 }
 
 void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4], int globalization,
+                         const double ls[3],
                          const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                          double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
-                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res)
+                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res, int32_t *qp_maxed)
 {
-    sqp_job j = {c, B, 0, max_iter, tol, globalization, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, status, sqp_iter, qp_iter, res};
+    sqp_job j = {c, B, 0, max_iter, tol, globalization, ls, qp_maxed, x0bar, p, yref, zl, Zl, x, u, sl, su, pi, lam, t, status, sqp_iter, qp_iter, res};
     atomic_init(&j.next, 0);
     if (nthreads <= 1) { sqp_worker(&j); return; }
     if (nthreads > 256) nthreads = 256;

@@ -105,13 +105,16 @@ void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p
  * (full steps), 1 = MERIT_BACKTRACKING (alpha *= 0.7 while the l1 merit function does not decrease, alpha_min 0.05).
  * pi/lam/t in/out (previous multipliers or zeros).  Returns 0 converged, 2 max_iter, 4 QP failure. */
 int orc_sqp_solve(const orc_config *c, int max_iter, const double tol[4], int globalization,
+                  const double ls[3] /* alpha_min, alpha_reduction, eps (accept when merit(a) < merit(0) + eps max(1,|merit(0)|)); NULL = 0.05, 0.7, 0 */,
                   const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                   double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
                   int32_t *sqp_iter, int32_t *qp_iter, double *res, double *stats);
 void orc_sqp_solve_batch(const orc_config *c, int64_t B, int nthreads, int max_iter, const double tol[4], int globalization,
+                         const double ls[3],
                          const double *x0bar, const double *p, const double *yref, const double *zl, const double *Zl,
                          double *x, double *u, double *sl, double *su, double *pi, double *lam, double *t,
-                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res);
+                         int32_t *status, int32_t *sqp_iter, int32_t *qp_iter, double *res,
+                         int32_t *qp_maxed /* per problem: QPs stopped by qp_iter_max (may be NULL) */);
 
 /* ---- QP export for validation (tests only) ------------------------------ */
 /* Builds the RTI QP of one problem and returns it densely so that numpy can

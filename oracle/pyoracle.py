@@ -167,18 +167,21 @@ def nlp_residuals(cfg, x0, p, yref, zl, Zl, x, u, sl, su, pi, lam, t):
     return res
 
 
-def sqp_solve_batch(cfg, x0, p, yref, zl, Zl, x, u, sl, su, pi=None, lam=None, t=None, max_iter=100, tol=NLP_TOL, nthreads=1, globalization=0):
-    """Batch-first arrays; iterate AND multipliers updated in place.  Returns dict(status, sqp_iter, qp_iter, res, pi, lam, t)."""
+def sqp_solve_batch(cfg, x0, p, yref, zl, Zl, x, u, sl, su, pi=None, lam=None, t=None, max_iter=100, tol=NLP_TOL, nthreads=1, globalization=0,
+                    ls=(0.05, 0.7, 0.0)):
+    """Batch-first arrays; iterate AND multipliers updated in place.  Returns dict(status, sqp_iter, qp_iter, res, pi, lam, t,
+    qp_maxed = number of QPs per problem that ran into qp_iter_max: such QPs are not at a KKT point, what follows is path dependent)."""
     B = x0.shape[0]; N, M = cfg.N, cfg.M
     pi = np.zeros((B, N, 5)) if pi is None else pi
     lam = np.zeros((B, N + 1, 12 + 4 * M)) if lam is None else lam
     t = np.zeros((B, N + 1, 12 + 4 * M)) if t is None else t
     status = np.zeros(B, np.int32); sqp_iter = np.zeros(B, np.int32); qp_iter = np.zeros(B, np.int32); res = np.zeros((B, 4))
-    tol_a = np.ascontiguousarray(tol, np.float64)
-    lib().orc_sqp_solve_batch(C.byref(cfg), C.c_int64(B), C.c_int(nthreads), C.c_int(max_iter), _p(tol_a), C.c_int(globalization),
+    tol_a = np.ascontiguousarray(tol, np.float64); ls_a = np.ascontiguousarray(ls, np.float64)
+    qp_maxed = np.zeros(B, np.int32)
+    lib().orc_sqp_solve_batch(C.byref(cfg), C.c_int64(B), C.c_int(nthreads), C.c_int(max_iter), _p(tol_a), C.c_int(globalization), _p(ls_a),
                               _p(x0), _p(p), _p(yref), _p(zl), _p(Zl), _p(x), _p(u), _p(sl), _p(su), _p(pi), _p(lam), _p(t),
-                              _pi(status), _pi(sqp_iter), _pi(qp_iter), _p(res))
-    return dict(status=status, sqp_iter=sqp_iter, qp_iter=qp_iter, res=res, pi=pi, lam=lam, t=t)
+                              _pi(status), _pi(sqp_iter), _pi(qp_iter), _p(res), _pi(qp_maxed))
+    return dict(status=status, sqp_iter=sqp_iter, qp_iter=qp_iter, res=res, pi=pi, lam=lam, t=t, qp_maxed=qp_maxed)
 
 
 def export_qp(cfg, x0, p, yref, zl, Zl, x, u, sl, su):
