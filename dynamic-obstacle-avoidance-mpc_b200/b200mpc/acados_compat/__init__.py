@@ -50,7 +50,9 @@ class AcadosOcp:
                                 lh_e=None, uh_e=None, Jsh=None, Jsh_e=None)
         self.solver_options = _Bag(qp_solver="PARTIAL_CONDENSING_HPIPM", hessian_approx="GAUSS_NEWTON",
                                    levenberg_marquardt=0.0, integrator_type="ERK", nlp_solver_type="SQP",
-                                   qp_solver_iter_max=50, tf=None)
+                                   qp_solver_iter_max=50, tf=None, nlp_solver_max_iter=100, nlp_solver_tol_stat=1e-6,
+                                   nlp_solver_tol_eq=1e-6, nlp_solver_tol_ineq=1e-6, nlp_solver_tol_comp=1e-6,
+                                   globalization="FIXED_STEP", alpha_min=0.05, alpha_reduction=0.7)
         self.parameter_values = None
 
 
@@ -74,8 +76,11 @@ def ocp_to_config(ocp: AcadosOcp) -> dict:
     at code-generation time."""
     N = int(ocp.dims.N)
     o, c, k = ocp.solver_options, ocp.cost, ocp.constraints
-    if o.nlp_solver_type != "SQP_RTI":
-        raise NotImplementedError(f"nlp_solver_type {o.nlp_solver_type!r}: only 'SQP_RTI' (robot_ocp_problem.py:130)")
+    if o.nlp_solver_type not in ("SQP_RTI", "SQP"):
+        raise NotImplementedError(f"nlp_solver_type {o.nlp_solver_type!r}: 'SQP_RTI' (robot_ocp_problem.py:130) or 'SQP'")
+    glob = {"FIXED_STEP": 0, "MERIT_BACKTRACKING": 1}.get(getattr(o, "globalization", "FIXED_STEP"))
+    if glob is None:
+        raise NotImplementedError(f"globalization {o.globalization!r}")
     if o.hessian_approx != "GAUSS_NEWTON" or o.qp_solver != "PARTIAL_CONDENSING_HPIPM":
         raise NotImplementedError("only GAUSS_NEWTON + PARTIAL_CONDENSING_HPIPM (robot_ocp_problem.py:126-127)")
     if c.cost_type != "LINEAR_LS" or c.cost_type_e != "LINEAR_LS":
@@ -110,7 +115,11 @@ def ocp_to_config(ocp: AcadosOcp) -> dict:
                 lm=float(o.levenberg_marquardt), W=list(np.diag(W)), W_e=list(np.diag(We)),
                 lbx=list(np.asarray(k.lbx, float)), ubx=list(np.asarray(k.ubx, float)),
                 lbu=list(np.asarray(k.lbu, float)), ubu=list(np.asarray(k.ubu, float)),
-                lh=float(lh[0]), uh=float(uh[0]), zu=float(zu[0]), Zu=float(Zu[0]))
+                lh=float(lh[0]), uh=float(uh[0]), zu=float(zu[0]), Zu=float(Zu[0]),
+                nlp_solver=1 if o.nlp_solver_type == "SQP" else 0, nlp_iter_max=int(getattr(o, "nlp_solver_max_iter", 100)),
+                nlp_tol=[float(getattr(o, "nlp_solver_tol_" + n, 1e-6)) for n in ("stat", "eq", "ineq", "comp")],
+                nlp_globalization=glob, ls_alpha_min=float(getattr(o, "alpha_min", 0.05)),
+                ls_alpha_reduction=float(getattr(o, "alpha_reduction", 0.7)))
 
 
 class AcadosOcpSolver:
@@ -190,6 +199,8 @@ class AcadosOcpSolver:
         t0 = time.perf_counter()
         status, qp_iter = self._solver.solve_host(f["x0"], f["p"], f["yref"], f["zl"], f["Zl"], f["x"], f["u"], f["sl"], f["su"])
         self._stats.update(time_tot=time.perf_counter() - t0, qp_iter=int(qp_iter[0]), status=int(status[0]))
+        if self._cfg["nlp_solver"] == 1:
+            self._stats["sqp_iter"] = int(self._solver.get_int("sqp_iter", 1, host=True)[0])
         return int(status[0])
 
     def get(self, stage, field):
@@ -204,6 +215,14 @@ class AcadosOcpSolver:
     def reset(self):
         for k in ("x", "u", "sl", "su"):
             self._f[k][:] = 0.0
+        if self._solver is not None:
+            self._solver.reset_multipliers(1)          # only the 'SQP' convergence test ever reads them
+
+    def get_residuals(self):
+        """[res_stat, res_eq, res_ineq, res_comp] of the last 'SQP' solve (acados: AcadosOcpSolver.get_residuals)"""
+        if self._solver is None or self._cfg["nlp_solver"] != 1:
+            raise Exception("AcadosOcpSolver.get_residuals(): needs nlp_solver_type 'SQP' and a solve()")
+        return self._solver.get("nlp_res", 1, host=True)[0].copy()
 
     def get_stats(self, field):
         if field in ("time_tot", "qp_iter", "sqp_iter", "status"):

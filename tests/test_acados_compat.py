@@ -47,7 +47,16 @@ def test_ocp_translation_and_validation():
     assert cfg["N"] == 20 and cfg["n_obst"] == 5 and cfg["integrator"] == 0 and cfg["lm"] == 2.0 and cfg["qp_iter_max"] == 50
     assert cfg["W"] == [2, 2, 2, 2, 0.15, 0.15] and cfg["W_e"] == [5, 5, 5, 5]
     assert cfg["lbx"] == [-7, -7, -10, -10] and cfg["ubu"] == [8, 8] and cfg["uh"] == 1e5
-    ocp.solver_options.nlp_solver_type = "SQP"
+    assert cfg["nlp_solver"] == 0                                           # 'SQP_RTI', robot_ocp_problem.py:130
+    ocp.solver_options.nlp_solver_type = "SQP"                              # the full-SQP mode
+    ocp.solver_options.nlp_solver_max_iter = 40; ocp.solver_options.nlp_solver_tol_stat = 1e-4
+    ocp.solver_options.globalization = "MERIT_BACKTRACKING"
+    cfg = acados_compat.ocp_to_config(ocp)
+    assert cfg["nlp_solver"] == 1 and cfg["nlp_iter_max"] == 40 and cfg["nlp_tol"] == [1e-4, 1e-6, 1e-6, 1e-6] and cfg["nlp_globalization"] == 1
+    ocp.solver_options.nlp_solver_type = "DDP"
+    with pytest.raises(NotImplementedError):
+        acados_compat.ocp_to_config(ocp)
+    ocp = _reference_ocp(); ocp.solver_options.globalization = "FUNNEL_L1PEN_LINESEARCH"
     with pytest.raises(NotImplementedError):
         acados_compat.ocp_to_config(ocp)
     ocp = _reference_ocp(); ocp.constraints.idxbx = np.array([0, 1, 2, 3])
@@ -155,3 +164,39 @@ def test_facade_closed_loop_equals_batched_solver(oracle):
             solver.set(j, "x", xo[j]); solver.set(j, "sl", slo[j]); solver.set(j, "su", suo[j])
         for j in range(N):
             solver.set(j, "u", uo[j])
+
+
+@pytest.mark.gpu
+def test_facade_sqp_mode(oracle):
+    """nlp_solver_type 'SQP' through the acados facade: statuses, get_stats('sqp_iter'), get_residuals(), reset()"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    N, M, tf = 20, 5, 2.0
+    ocp = _reference_ocp(N, tf)
+    o = ocp.solver_options
+    o.nlp_solver_type, o.nlp_solver_max_iter = "SQP", 400
+    o.nlp_solver_tol_stat = o.nlp_solver_tol_eq = o.nlp_solver_tol_ineq = o.nlp_solver_tol_comp = 1e-5
+    solver = acados_compat.AcadosOcpSolver(ocp, json_file="acados_ocp.json")
+    sc = world.random_scenarios(4, world.MpcDims(N, M, tf), seed=33)
+    b = 1
+    for i in range(N + 1):
+        solver.set(i, "p", sc["p"][b, i]); solver.cost_set(i, "zl", sc["zl"][b, i]); solver.cost_set(i, "Zl", sc["Zl"][b, i])
+        solver.cost_set(i, "yref", sc["yref"][b, i] if i < N else sc["yref"][b, i, :4])
+        solver.set(i, "x", sc["x"][b, i])
+    solver.set(0, "lbx", sc["x0"][b]); solver.set(0, "ubx", sc["x0"][b])
+    stat = solver.solve()
+    cfg = oracle.default_config(N, M, tf)
+    w = {k: sc[k][b:b + 1].copy() for k in ("x", "u", "sl", "su")}
+    r = oracle.sqp_solve_batch(cfg, sc["x0"][b:b + 1], sc["p"][b:b + 1], sc["yref"][b:b + 1], sc["zl"][b:b + 1], sc["Zl"][b:b + 1],
+                               w["x"], w["u"], w["sl"], w["su"], max_iter=400, tol=(1e-5,) * 4)
+    assert stat == r["status"][0] == 0
+    assert abs(solver.get_stats("sqp_iter") - r["sqp_iter"][0]) <= 1 and solver.get_stats("sqp_iter") > 5
+    assert (solver.get_residuals() < 1e-5).all()
+    assert np.abs(solver.get(0, "u") - w["u"][0, 0]).max() < 1e-4
+    assert solver.solve() == 0 and solver.get_stats("sqp_iter") == 0        # already converged: no QP
+    keep = {k: solver._f[k].copy() for k in ("x", "u", "sl", "su")}
+    solver.reset()                                                          # forgets the multipliers as well
+    for k, v in keep.items():
+        solver._f[k][:] = v
+    assert solver.solve() == 0 and solver.get_stats("sqp_iter") >= 1        # stationarity must be re-established
