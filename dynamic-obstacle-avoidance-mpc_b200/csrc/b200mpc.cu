@@ -181,14 +181,15 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     // kernel selection.  The warp-per-problem kernel keeps the cross-lane part of a problem in shared
     // memory; the node-private rows go to shared memory too (kernel 3, needs the whole problem to fit) or,
     // per field, to an L2-resident block of global memory per resident CTA (kernel 2, any N <= 128).
-    unsigned smask = B2_WPP_ALL_GLOBAL;
+    unsigned smask = B2_WPP_ALL_GLOBAL, smask_sqp = B2_WPP_ALL_GLOBAL;      // layouts of wpp_fn / wpp_fn_sqp
     h->wpp_fn = nullptr;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     const bool ref_dims = (M == 5 && N == 20);          // the reference's configuration (world_specification.py:44-48)
+    const bool ref_dims_short = (M == 5 && N == 10);    // the reference's other recorded setting: TF = 1 s => N_SOLV = 10
     const bool long_dims = (M == 20 && N == 100);       // BASELINE.json config 4
     if (cfg->kernel == 3) {
-        smask = B2_WPP_ALL_SHARED;
+        smask = smask_sqp = B2_WPP_ALL_SHARED;
         if (b2_wpp_smem_bytes(N, M, smask) > (size_t)max_smem) {
             b2mpc_destroy(h);
             return fail(B2MPC_EINVAL, "all-shared warp kernel needs %zu B > %d B of shared memory", b2_wpp_smem_bytes(N, M, smask), max_smem);
@@ -200,7 +201,9 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->kernel = 1;
     } else {
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL>
-                  : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_ALL_GLOBAL> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
+                  : ref_dims_short ? b2_rti_solve_wpp<5, 10, B2_WPP_ALL_GLOBAL>
+                  : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_LONG> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
+        if (long_dims) smask = B2_WPP_LONG;                  // v and pi in global memory too: 3 CTAs/SM instead of 2
         h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL, true>;
         h->kernel = 2;
     }
@@ -213,7 +216,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     h->prm.WS = h->ws;
     if (h->kernel != 1) {
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
-        h->wpp_smem_sqp = b2_wpp_smem_bytes(N, M, smask, true);
+        h->wpp_smem_sqp = b2_wpp_smem_bytes(N, M, smask_sqp, true);
         if (h->wpp_smem_sqp > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
         if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 2 * B2_ORDER_MAXKEYS + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
         cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
@@ -230,8 +233,8 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->wpp_grid = occ * sms;
         if (h->wpp_grid > h->Bm) h->wpp_grid = h->Bm;
         h->prm.wpriv_stride = b2_wpp_priv_doubles(N, M, smask);              // RTI launches keep their compact blocks (L2 footprint)
-        h->wpriv_stride_sqp = b2_wpp_priv_doubles(N, M, smask, true);
-        h->wpriv_bytes = sizeof(double) * h->wpriv_stride_sqp * (size_t)h->wpp_grid;
+        h->wpriv_stride_sqp = b2_wpp_priv_doubles(N, M, smask_sqp, true);
+        h->wpriv_bytes = sizeof(double) * (h->wpriv_stride_sqp > h->prm.wpriv_stride ? h->wpriv_stride_sqp : h->prm.wpriv_stride) * (size_t)h->wpp_grid;
         if (h->wpriv_bytes) {
             if (cudaMalloc(&h->wpriv, h->wpriv_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(node-private rows, %zu B) failed", h->wpriv_bytes); }
             cudaMemset(h->wpriv, 0, h->wpriv_bytes);

@@ -42,23 +42,30 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
        PF_CX, PF_CY, PF_LG, PF_UG, PF_ZLQ, PF_ZZLQ, PF_SLI, PF_SUI, PF_SL, PF_SU,
        PF_LRGSL, PF_LRGSU, PF_DSL, PF_DSU, PF_DLI, PF_DUI,
        PF_WPI, PF_WLAM,                                      // merit-function weights of the SQP line search (SQP kernels only)
+       PF_V, PF_PI,                                          // QP iterate v (7 rows) and pi (5): touched by the owner lane and its
+                                                             // neighbours k-1 / k+1 only, never inside a sequential sweep
        PF_COUNT };
-#define B2_WPP_ALL_SHARED 0x7ffffffu
+#define B2_WPP_ALL_SHARED 0x1fffffffu
 // Placement used by default: EVERY node-private field in global memory.  Measured on B200 (N=20, M=5, 4096 problems,
 // profiles/experiments/r01_hybrid_layout.md): all global, 12 CTAs/SM 11.6 ms; lam,t shared, 7 CTAs/SM 13.1 ms;
 // lam,t,1/t,dlam shared, 5 CTAs/SM 14.3 ms; all shared, 4 CTAs/SM 12.7 ms.
-#define B2_WPP_ALL_GLOBAL 0u
+#define B2_WPP_ALL_GLOBAL ((1u << PF_V) | (1u << PF_PI))   // ... except v and pi (12 rows), which stay in shared memory
+// Long horizons (N = 100: 103 shared rows x 101 nodes = 85 KB, 2 CTAs/SM): v and pi in global memory as well -> 91 rows,
+// 73.8 KB, 3 CTAs/SM.
+#define B2_WPP_LONG 0u
 #ifndef B2_WPP_MINB
 #define B2_WPP_MINB 12          // resident CTAs per SM the N=20 layout is compiled for (register cap 65536/32/MINB = 170)
 #endif
 
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu, v, pi;       // shared-memory rows read across lanes
+    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu;             // shared-memory rows read across lanes
     int pf[PF_COUNT];                                                           // row of each private field in ITS space
     int total;                                                                  // shared-memory rows (incl. private fields placed there)
     int gtotal;                                                                 // global-memory rows
     __host__ __device__ static int pf_rows(int f, int M, bool sqp)
     {
+        if (f == PF_V) return 7;
+        if (f == PF_PI) return 5;
         if (f >= PF_WPI) return !sqp ? 0 : f == PF_WPI ? 5 : 12 + 4 * M;
         return f <= PF_DT ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
     }
@@ -67,9 +74,12 @@ struct WOff {
         int o = 0;
         sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
         cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5; lu = o; o += 2;
-        v = o; o += 7; pi = o; o += 5;
         int g = 0;
-        for (int f = 0; f < PF_COUNT; f++) {
+        for (int f = PF_V; f <= PF_PI; f++) {                   // first: their rows are where they have always been
+            if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); }
+            else { pf[f] = g; g += pf_rows(f, M, sqp); }
+        }
+        for (int f = 0; f < PF_V; f++) {
             if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); }
             else { pf[f] = g; g += pf_rows(f, M, sqp); }
         }
@@ -158,6 +168,17 @@ struct WppSolver {
     {
         if ((SMASK >> F) & 1u) return sm[(o.pf[F] + i) * NS + k];
         return gm[(size_t)((o.pf[F] + i) * GS + k)];
+    }
+    // rows of v / pi at node kk (the owner's or a neighbour's)
+    __device__ __forceinline__ double& VV(int i, int kk) const
+    {
+        if ((SMASK >> PF_V) & 1u) return sm[(o.pf[PF_V] + i) * NS + kk];
+        return gm[(size_t)((o.pf[PF_V] + i) * GS + kk)];
+    }
+    __device__ __forceinline__ double& PP(int i, int kk) const
+    {
+        if ((SMASK >> PF_PI) & 1u) return sm[(o.pf[PF_PI] + i) * NS + kk];
+        return gm[(size_t)((o.pf[PF_PI] + i) * GS + kk)];
     }
     __device__ __forceinline__ bool box_on(int s, int kk) const { return s < 2 ? (kk < N) : (kk > 0 && kk < N); }
     __device__ __forceinline__ double scal(int kk) const { return kk < N ? p.dt : 1.0; }
@@ -251,9 +272,9 @@ struct WppSolver {
                 Q<PF_SL>(j) = 0.0; Q<PF_SU>(j) = 0.0; Q<PF_DSL>(j) = 0.0; Q<PF_DSU>(j) = 0.0;
             }
 #pragma unroll
-            for (int i = 0; i < 7; i++) S(o.v + i, k) = v[i];
+            for (int i = 0; i < 7; i++) VV(i, k) = v[i];
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(o.pi + i, k) = 0.0;
+            for (int i = 0; i < 5; i++) PP(i, k) = 0.0;
         }
         __syncwarp();
     }
@@ -274,10 +295,10 @@ struct WppSolver {
     {
         for (k = lane; k <= N; k += 32) {
 #pragma unroll
-            for (int i = 0; i < 7; i++) S(o.v + i, k) += a * S(o.dv + i, k);
+            for (int i = 0; i < 7; i++) VV(i, k) += a * S(o.dv + i, k);
             if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) S(o.pi + i, k) += a * S(o.dpi + i, k);
+                for (int i = 0; i < 5; i++) PP(i, k) += a * S(o.dpi + i, k);
             }
         }
         __syncwarp();
@@ -287,21 +308,21 @@ struct WppSolver {
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
 #pragma unroll
-            for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
+            for (int i = 0; i < 7; i++) { v[i] = VV(i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
             double sv[10];
             if (k < N) {
 #pragma unroll
                 for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, k);
                 double pk[5], bt[7];
 #pragma unroll
-                for (int i = 0; i < 5; i++) pk[i] = S(o.pi + i, k);
+                for (int i = 0; i < 5; i++) pk[i] = PP(i, k);
                 b2_bat_mul(sv, p.dt, p.dt2h, pk, bt);
 #pragma unroll
                 for (int i = 0; i < 7; i++) rg[i] += bt[i];
             }
             if (k > 0) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) rg[2 + i] -= S(o.pi + i, k - 1);
+                for (int i = 0; i < 5; i++) rg[2 + i] -= PP(i, k - 1);
             }
 #pragma unroll
             for (int s = 0; s < 6; s++) {
@@ -390,7 +411,7 @@ struct WppSolver {
                 b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
-                    rb[i] += Q<PF_B>(i) - S(o.v + 2 + i, k + 1);
+                    rb[i] += Q<PF_B>(i) - VV(2 + i, k + 1);
                     S(o.rb + i, k) = rb[i];
                     n1 = fmax(n1, fabs(rb[i]));
                 }
@@ -558,7 +579,7 @@ struct WppSolver {
             } else {
                 double v[7];
 #pragma unroll
-                for (int i = 0; i < 7; i++) { v[i] = S(o.v + i, k); gt[i] = Q<PF_RG>(i); }
+                for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
 #pragma unroll
                 for (int s = 0; s < 6; s++) {
                     if (!box_on(s, k)) continue;
@@ -713,7 +734,7 @@ struct WppSolver {
         double v[7], dv[7], cv[7];
 #pragma unroll
         for (int i = 0; i < 7; i++) {
-            v[i] = S(o.v + i, k);
+            v[i] = VV(i, k);
             dv[i] = S(o.dv + i, k);
             cv[i] = 0.0;
             if (MODE == XP_REFINE) { cv[i] = S(o.cv + i, k); dv[i] += cv[i]; S(o.dv + i, k) = dv[i]; }
@@ -982,7 +1003,7 @@ struct WppSolver {
             double xk[5], uk[2] = {0.0, 0.0};
             const double ax = k == 0 ? 1.0 : al;
 #pragma unroll
-            for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b] + ax * S(o.v + 2 + i, k);
+            for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b] + ax * VV(2 + i, k);
             const double* yr = p.YREF + ((size_t)k * 6) * Bm + b;
             const double sc = scal(k);
             const double* Wc = k < N ? p.Wg : p.Wge;
@@ -990,15 +1011,15 @@ struct WppSolver {
                        + Wc[5] * (xk[3] - yr[2 * Bm]) * (xk[3] - yr[2 * Bm]) + Wc[6] * (xk[4] - yr[3 * Bm]) * (xk[4] - yr[3 * Bm]);
             double mk = 0.0;
             if (k < N) {
-                uk[0] = p.U[((size_t)k * 2 + 0) * Bm + b] + al * S(o.v + 0, k);
-                uk[1] = p.U[((size_t)k * 2 + 1) * Bm + b] + al * S(o.v + 1, k);
+                uk[0] = p.U[((size_t)k * 2 + 0) * Bm + b] + al * VV(0, k);
+                uk[1] = p.U[((size_t)k * 2 + 1) * Bm + b] + al * VV(1, k);
                 cst += Wc[0] * (uk[0] - yr[4 * Bm]) * (uk[0] - yr[4 * Bm]) + Wc[1] * (uk[1] - yr[5 * Bm]) * (uk[1] - yr[5 * Bm]);
                 double xn[5], sv[10];
                 if (p.integrator == 1) model_rk4_step(xk, uk, p.dt, xn, sv);
                 else model_gl4_step(xk, uk, p.dt, xn, sv);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
-                    const double xn1 = p.X[((size_t)(k + 1) * 5 + i) * Bm + b] + al * S(o.v + 2 + i, k + 1);
+                    const double xn1 = p.X[((size_t)(k + 1) * 5 + i) * Bm + b] + al * VV(2 + i, k + 1);
                     mk += Q<PF_WPI>(i) * fabs(xn[i] - xn1);
                 }
             }
@@ -1035,7 +1056,7 @@ struct WppSolver {
             if (k < N) {
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
-                    const double a = fabs(S(o.pi + i, k));
+                    const double a = fabs(PP(i, k));
                     Q<PF_WPI>(i) = first ? a : fmax(a, 0.5 * (Q<PF_WPI>(i) + a));
                 }
             }
@@ -1124,14 +1145,14 @@ struct WppSolver {
             for (k = lane; k <= N; k += 32) {
                 const double ax = k == 0 ? 1.0 : al;
 #pragma unroll
-                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += ax * S(o.v + 2 + i, k);
+                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += ax * VV(2 + i, k);
                 if (k < N) {
-                    p.U[((size_t)k * 2 + 0) * Bm + b] += al * S(o.v + 0, k);
-                    p.U[((size_t)k * 2 + 1) * Bm + b] += al * S(o.v + 1, k);
+                    p.U[((size_t)k * 2 + 0) * Bm + b] += al * VV(0, k);
+                    p.U[((size_t)k * 2 + 1) * Bm + b] += al * VV(1, k);
 #pragma unroll
                     for (int i = 0; i < 5; i++) {
                         double* d = p.PI + ((size_t)k * 5 + i) * Bm + b;
-                        *d += al * (S(o.pi + i, k) - *d);
+                        *d += al * (PP(i, k) - *d);
                     }
                 }
 #pragma unroll JU
@@ -1150,10 +1171,10 @@ struct WppSolver {
         for (k = lane; k <= N; k += 32) {
             if (status == 0) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += S(o.v + 2 + i, k);
+                for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += VV(2 + i, k);
                 if (k < N) {
-                    p.U[((size_t)k * 2 + 0) * Bm + b] += S(o.v + 0, k);
-                    p.U[((size_t)k * 2 + 1) * Bm + b] += S(o.v + 1, k);
+                    p.U[((size_t)k * 2 + 0) * Bm + b] += VV(0, k);
+                    p.U[((size_t)k * 2 + 1) * Bm + b] += VV(1, k);
                 }
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
@@ -1163,7 +1184,7 @@ struct WppSolver {
             }
             if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = S(o.pi + i, k);
+                for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = PP(i, k);
             }
             for (int i = 0; i < nct; i++) {
                 p.LAM[((size_t)k * nct + i) * Bm + b] = Q<PF_LAM>(i);

@@ -3,7 +3,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dynamic-obstacle-avoidance-mpc_b200"))
 import torch
-from b200mpc import BatchedMpcSolver, world
+from b200mpc import BatchedMpcSolver, world, capi
+if os.environ.get('B2MPC_LIB'):
+    capi.LIB_PATH = os.path.join(ROOT, os.environ['B2MPC_LIB'])
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 N, M, tf = (int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5])) if len(sys.argv) > 5 else (100, 20, 5.0)
