@@ -115,6 +115,7 @@ static void fill_params(b2mpc* h)
     }
     for (int i = 0; i < 4; i++) { p.lbx[i] = c.lbx[i]; p.ubx[i] = c.ubx[i]; }
     for (int i = 0; i < 2; i++) { p.lbu[i] = c.lbu[i]; p.ubu[i] = c.ubu[i]; }
+    for (int i = 0; i < 6; i++) { p.lb6[i] = i < 2 ? c.lbu[i] : c.lbx[i - 2]; p.ub6[i] = i < 2 ? c.ubu[i] : c.ubx[i - 2]; }
     p.r2 = c.r2; p.lh = c.lh; p.uh = c.uh; p.zu = c.zu; p.Zu = c.Zu;
     p.mu0 = c.mu0; p.alpha_min = c.alpha_min; p.res_g_max = c.res_g_max; p.res_b_max = c.res_b_max;
     p.res_d_max = c.res_d_max; p.res_m_max = c.res_m_max; p.reg_prim = c.reg_prim;

@@ -54,6 +54,7 @@ struct B2Params {
     double Hd[7], Hde[7];        // Hessian diagonals (stage / terminal), LM included
     double Wg[7], Wge[7];        // gradient weights: g = Wg * (y - yref) in v order (psi entry 0)
     double lbx[4], ubx[4], lbu[2], ubu[2];
+    double lb6[6], ub6[6];       // the same bounds in box-slot order [u_a, u_alpha, x, y, v, omega]
     double r2, lh, uh, zu, Zu;
     double mu0, alpha_min, res_g_max, res_b_max, res_d_max, res_m_max;
     double reg_prim, lam_min, t_min, tau_min, thr0;

@@ -53,6 +53,15 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 // Long horizons (N = 100: 103 shared rows x 101 nodes = 85 KB, 2 CTAs/SM): v and pi in global memory as well -> 91 rows,
 // 73.8 KB, 3 CTAs/SM.
 #define B2_WPP_LONG 0u
+// The six box slots of a node: unrolled by default.  -DB2_WPP_ROLL_BOX walks them with a rolled loop (select chains /
+// predicated adds instead of compile-time register indices; same arithmetic, bit-identical results): 20 KB less code
+// (8104 -> 6936 instructions).  Measured on B200: N=20 +2.0 % at 32 768 problems, -0.2 % at 4096; N=10 -2.5 %; N=100 -10 %
+// (more instructions executed; only the 12-CTA/SM N=20 kernel is instruction-fetch bound enough to profit).
+#ifdef B2_WPP_ROLL_BOX
+#define B2_BOX_LOOP _Pragma("unroll 1")
+#else
+#define B2_BOX_LOOP _Pragma("unroll")
+#endif
 #ifndef B2_WPP_MINB
 #define B2_WPP_MINB 12          // resident CTAs per SM the N=20 layout is compiled for (register cap 65536/32/MINB = 170)
 #endif
@@ -185,8 +194,7 @@ struct WppSolver {
     __device__ __forceinline__ void box_bounds(int s, double& lb, double& ub) const
     {
         const double xv = Q<PF_XU>(s);
-        if (s < 2) { lb = p.lbu[s] - xv; ub = p.ubu[s] - xv; }
-        else { lb = p.lbx[s - 2] - xv; ub = p.ubx[s - 2] - xv; }
+        lb = p.lb6[s] - xv; ub = p.ub6[s] - xv;          // [lbu, lbx] / [ubu, ubx] in slot order
     }
 
     // ---- preparation + cold-start initialisation: lane k handles node k ----------------------------
@@ -279,6 +287,29 @@ struct WppSolver {
         __syncwarp();
     }
 
+    // Element of a per-node register array (v order [u_a,u_alpha,x,y,psi,v,omega]) that belongs to box slot s (the slots
+    // skip psi).  In the ROLLED box loops s is a run-time value: a select chain / predicated adds instead of dynamic
+    // indexing (which would push the arrays to local memory); with a compile-time s both fold to a[iv].
+    __device__ __forceinline__ static double slot_get(const double* a, int s)
+    {
+        double r = a[0];
+        if (s == 1) r = a[1];
+        if (s == 2) r = a[2];
+        if (s == 3) r = a[3];
+        if (s == 4) r = a[5];
+        if (s == 5) r = a[6];
+        return r;
+    }
+    __device__ __forceinline__ static void slot_add(double* a, int s, double x)
+    {
+        if (s == 0) a[0] += x;
+        if (s == 1) a[1] += x;
+        if (s == 2) a[2] += x;
+        if (s == 3) a[3] += x;
+        if (s == 4) a[5] += x;
+        if (s == 5) a[6] += x;
+    }
+
     // g_i(v,s) of the box constraints (rd_i = g_i - t_i)
     __device__ __forceinline__ double g_box_l(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return v[b2_slot2v(s)] - lb; }
     __device__ __forceinline__ double g_box_u(int s, const double* v) const { double lb, ub; box_bounds(s, lb, ub); return ub - v[b2_slot2v(s)]; }
@@ -324,10 +355,9 @@ struct WppSolver {
 #pragma unroll
                 for (int i = 0; i < 5; i++) rg[2 + i] -= PP(i, k - 1);
             }
-#pragma unroll
+            B2_BOX_LOOP
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
-                const int iv = b2_slot2v(s);
                 const int il = o_lb + s, iu = o_ub + s;
                 double ll = Q<PF_LAM>(il) + a * Q<PF_DD>(il), lu_ = Q<PF_LAM>(iu) + a * Q<PF_DD>(iu);
                 double tl = Q<PF_T>(il) + a * Q<PF_DT>(il), tu = Q<PF_T>(iu) + a * Q<PF_DT>(iu);
@@ -336,8 +366,11 @@ struct WppSolver {
                 if (tl <= p.t_min) tl = p.t_min;
                 if (tu <= p.t_min) tu = p.t_min;
                 Q<PF_LAM>(il) = ll; Q<PF_LAM>(iu) = lu_; Q<PF_T>(il) = tl; Q<PF_T>(iu) = tu;
-                rg[iv] += -ll + lu_;
-                const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+                slot_add(rg, s, -ll + lu_);
+                double lb, ub;
+                box_bounds(s, lb, ub);
+                const double vv = slot_get(v, s);
+                const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
                 n2 = fmax(n2, fmax(fabs(rdl), fabs(rdu)));
                 const double ml = ll * tl, mu_ = lu_ * tu;
                 n3 = fmax(n3, fmax(fabs(ml), fabs(mu_)));
@@ -345,8 +378,8 @@ struct WppSolver {
                 const double rlu = 1.0 / (tl * tu);                    // one division per pair: 1/tl = tu/(tl tu)
                 const double til = b2_rcp_polish(tl, rlu * tu), tiu = b2_rcp_polish(tu, rlu * tl);
                 Q<PF_TINV>(il) = til; Q<PF_TINV>(iu) = tiu;
-                Hx[iv] += ll * til + lu_ * tiu;
-                gt[iv] += (ml + ll * rdl) * til - (mu_ + lu_ * rdu) * tiu;
+                slot_add(Hx, s, ll * til + lu_ * tiu);
+                slot_add(gt, s, (ml + ll * rdl) * til - (mu_ + lu_ * rdu) * tiu);
             }
             const double Zuq = sc * p.Zu;
 #pragma unroll JU
@@ -493,7 +526,9 @@ struct WppSolver {
             // (the power of two keeps sigma in [1, 2^7)), and each lane normalises its own column once at
             // the end: L_ic = S_ic / sqrt(sigma_c p_c).  Non-positive pivot -> zero column, as BLASFEO.
             double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
-#pragma unroll
+            // rolled: the unrolled 7 columns made the loop body 5.9 KB, the size of an L0 instruction cache that three
+            // warps share (measured +0.6 % at 4096 problems, +2.2 % at 32 768; same arithmetic)
+#pragma unroll 1
             for (int c = 0; c < 7; c++) {
                 const double pv_ = b2_bcast(m, c * (c + 1) / 2 + c);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
@@ -580,15 +615,18 @@ struct WppSolver {
                 double v[7];
 #pragma unroll
                 for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
-#pragma unroll
+                B2_BOX_LOOP
                 for (int s = 0; s < 6; s++) {
                     if (!box_on(s, k)) continue;
                     const int il = o_lb + s, iu = o_ub + s;
                     const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
-                    const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
+                    double lb, ub;
+                    box_bounds(s, lb, ub);
+                    const double vv = slot_get(v, s);
+                    const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
                     const double ql = (rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * rdl) * Q<PF_TINV>(il);
                     const double qu = (rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * rdu) * Q<PF_TINV>(iu);
-                    gt[b2_slot2v(s)] += ql - qu;
+                    slot_add(gt, s, ql - qu);
                 }
                 const double Zuq = sc * p.Zu;
 #pragma unroll JU
@@ -743,14 +781,16 @@ struct WppSolver {
 #pragma unroll
             for (int i = 0; i < 5; i++) S(o.dpi + i, k) += S(o.cpi + i, k);
         }
-#pragma unroll
+        B2_BOX_LOOP
         for (int s = 0; s < 6; s++) {
             if (!box_on(s, k)) continue;
-            const int iv = b2_slot2v(s);
             const int il = o_lb + s, iu = o_ub + s;
             const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
-            const double rdl = g_box_l(s, v) - tl, rdu = g_box_u(s, v) - tu;
-            const double dtl = dv[iv] + rdl, dtu = -dv[iv] + rdu;
+            double lb, ub;
+            box_bounds(s, lb, ub);
+            const double vv = slot_get(v, s), dvv = slot_get(dv, s);
+            const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
+            const double dtl = dvv + rdl, dtu = -dvv + rdu;
             double dll, dlu;
             if (MODE == XP_SOLVE) {
                 dll = -(rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * dtl) * Q<PF_TINV>(il);
@@ -759,8 +799,9 @@ struct WppSolver {
                 Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
                 Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
             } else if (MODE == XP_REFINE) {
-                dll = Q<PF_DD>(il) - ll * cv[iv] * Q<PF_TINV>(il);
-                dlu = Q<PF_DD>(iu) + lu_ * cv[iv] * Q<PF_TINV>(iu);
+                const double cvv = slot_get(cv, s);
+                dll = Q<PF_DD>(il) - ll * cvv * Q<PF_TINV>(il);
+                dlu = Q<PF_DD>(iu) + lu_ * cvv * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
                 Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
             } else {
@@ -768,7 +809,7 @@ struct WppSolver {
             }
             consume<MODE>(il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
             consume<MODE>(iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
-            if (MODE == XP_LIN) lrg[iv] += -dll + dlu;
+            if (MODE == XP_LIN) slot_add(lrg, s, -dll + dlu);
         }
 #pragma unroll JU
         for (int j = 0; j < M; j++) {
@@ -1209,8 +1250,13 @@ struct WppSolver {
     }
 };
 
+#ifdef B2_EXP_MAXNREG          // experiment: register budget instead of a minimum CTA count
+#define B2_WPP_BOUNDS(NT, SMASK) __maxnreg__(B2_EXP_MAXNREG)
+#else
+#define B2_WPP_BOUNDS(NT, SMASK) __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_SHARED) ? B2_WPP_MINB : 1)
+#endif
 template <int MT, int NT, unsigned SMASK, bool SQP = false>
-__global__ void __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_SHARED) ? B2_WPP_MINB : 1) b2_rti_solve_wpp(const B2Params p)
+__global__ void B2_WPP_BOUNDS(NT, SMASK) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
     double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows
