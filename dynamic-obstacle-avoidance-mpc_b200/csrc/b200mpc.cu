@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -51,6 +52,8 @@ struct b2mpc {
     size_t wpp_smem;
     void (*wpp_fn)(const B2Params);  // selected instantiation of the warp kernel
     int wpp_grid;                    // resident CTAs (SMs x occupancy): the persistent grid
+    int l2_persist;                  // experiment (B2MPC_L2_PERSIST=1): launch with an L2 access-policy window over wpriv
+    float l2_hit_ratio;
     double* wpriv;                   // node-private rows of the resident CTAs
     size_t wpriv_bytes;
     void (*wpp_fn_small)(const B2Params);   // auto mode: all-shared instantiation for batches that fit the GPU at once
@@ -241,6 +244,21 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
             cudaMemset(h->wpriv, 0, h->wpriv_bytes);
         }
         h->prm.WPRIV = h->wpriv;
+        if (const char* e = getenv("B2MPC_L2_PERSIST")) {
+            if (atoi(e) > 0) {
+                cudaDeviceProp prop;
+                cudaGetDeviceProperties(&prop, cfg->device);
+                size_t want = sizeof(double) * h->prm.wpriv_stride * (size_t)h->wpp_grid;
+                size_t lim = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+                if (atoi(e) > 1) lim = lim * atoi(e) / 100;                    // B2MPC_L2_PERSIST=<percent of the maximum>
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim);
+                h->l2_persist = 1;
+                h->l2_hit_ratio = want > lim ? (float)((double)lim / (double)want) : 1.0f;
+                if ((size_t)prop.accessPolicyMaxWindowSize < want) h->l2_persist = 0;
+                fprintf(stderr, "[b200mpc] L2 persist: want %zu B, set-aside %zu B (max %d), window max %d, hitRatio %.2f, on=%d\n",
+                        want, lim, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize, h->l2_hit_ratio, h->l2_persist);
+            }
+        }
         // auto mode: a batch that fits the GPU in one wave of all-shared CTAs (<= 4 per SM at N=20, M=5) has no use
         // for more resident CTAs, and the all-shared layout has the shorter per-problem latency (no L2 round trips):
         // single closed-loop episodes (BASELINE config 1) and small batches take that instantiation.
@@ -739,6 +757,19 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
             h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
         } else {
             const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);   // persistent: one warp-CTA per resident slot
+            if (h->l2_persist && h->wpriv_bytes) {
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(blocks); lc.blockDim = dim3(32); lc.dynamicSmemBytes = h->wpp_smem; lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+                at[0].val.accessPolicyWindow.base_ptr = h->wpriv;
+                at[0].val.accessPolicyWindow.num_bytes = sizeof(double) * h->prm.wpriv_stride * (size_t)blocks;
+                at[0].val.accessPolicyWindow.hitRatio = h->l2_hit_ratio;
+                at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                lc.attrs = at; lc.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&lc, h->wpp_fn, (const B2Params)p));
+            } else
             h->wpp_fn<<<blocks, 32, h->wpp_smem, st>>>(p);
         }
     } else {
