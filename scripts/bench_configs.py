@@ -41,7 +41,9 @@ out["config1_single_episode"] = dict(control_steps=steps, reached=bool(res[2][0]
 ocp.solver.close()
 # config 2/3: per-GPU batches of the 262144-scenario sweep (8 / 4 / 2 GPUs -> 32768 / 65536 / 131072 per GPU)
 out["config3_per_gpu_share"] = [time_solve(20, 5, 2.0, B, reps=2) for B in (4096, 32768, 65536, 131072)]
-# config 4: long horizon, many obstacles (generic thread-per-problem kernel)
+# the reference's other recorded setting: TF = 1 s => N_SOLV = 10 (dedicated instantiation)
+out["ref_setting_tf1_n10"] = [time_solve(10, 5, 1.0, B, reps=3) for B in (4096, 32768)]
+# config 4: long horizon, many obstacles (warp kernel, v/pi rows in global memory: 3 CTAs/SM)
 out["config4_long_horizon"] = [time_solve(100, 20, 5.0, B, reps=2) for B in (4096,)]
 # closed loop on device: 4096 environments x 50 control steps
 B = 4096
