@@ -243,3 +243,26 @@ def test_auto_mode_picks_the_layout_by_batch_size(torch_cuda):
     for n, twin in ((96, 3), (B, 2)):
         a, b = run(0, n), run(twin, n)
         assert all(np.array_equal(p, q) for p, q in zip(a, b)), (n, twin)
+
+
+def test_maximum_dimensions_and_single_problem(torch_cuda, oracle):
+    """the limits of the C-ABI (B2MPC_MAX_N = 128 nodes, B2MPC_MAX_OBST = 32 obstacles: five lane passes, 140 constraints
+    per node, run-time-dimension instantiation) and the smallest batch (one problem, one node short of nothing: N = 1)"""
+    from b200mpc import BatchedMpcSolver, capi
+    dims = world.MpcDims(128, 32, 6.4)
+    B = 6
+    sc = world.random_scenarios(B, dims, seed=3)
+    out, ref = _solve_both(torch_cuda, oracle, dims, sc, B, qp_iter_max=100)     # 32 obstacles: 50-69 iterations on the CPU
+    assert (out["status"] == ref["status"]).all() and (ref["qp_iter"] < 100).all()
+    assert np.abs(out["qp_iter"] - ref["qp_iter"]).max() <= 2 and np.mean(out["qp_iter"] == ref["qp_iter"]) >= 0.5
+    assert _rel_rows(out["u"], ref["u"]).max() < REL_TOL and _rel_rows(out["x"], ref["x"]).max() < REL_TOL
+    dims1 = world.MpcDims(1, 1, 0.1)
+    sc1 = world.random_scenarios(1, dims1, seed=4)
+    out1, ref1 = _solve_both(torch_cuda, oracle, dims1, sc1, 1)
+    assert out1["status"][0] == ref1["status"][0] and abs(int(out1["qp_iter"][0]) - int(ref1["qp_iter"][0])) <= 1
+    if ref1["qp_iter"][0] < 50:
+        assert _rel(out1["u"], ref1["u"]) < REL_TOL and _rel(out1["x"], ref1["x"]) < REL_TOL
+    with pytest.raises(capi.B2mpcError):
+        BatchedMpcSolver(129, 5, 6.45, max_batch=2)
+    with pytest.raises(capi.B2mpcError):
+        BatchedMpcSolver(20, 33, 2.0, max_batch=2)
