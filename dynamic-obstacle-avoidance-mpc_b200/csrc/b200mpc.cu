@@ -185,7 +185,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     // kernel selection.  The warp-per-problem kernel keeps the cross-lane part of a problem in shared
     // memory; the node-private rows go to shared memory too (kernel 3, needs the whole problem to fit) or,
     // per field, to an L2-resident block of global memory per resident CTA (kernel 2, any N <= 128).
-    unsigned smask = B2_WPP_ALL_GLOBAL, smask_sqp = B2_WPP_ALL_GLOBAL;      // layouts of wpp_fn / wpp_fn_sqp
+    unsigned long long smask = B2_WPP_ALL_GLOBAL, smask_sqp = B2_WPP_ALL_GLOBAL;      // layouts of wpp_fn / wpp_fn_sqp
     h->wpp_fn = nullptr;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -207,7 +207,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL>
                   : ref_dims_short ? b2_rti_solve_wpp<5, 10, B2_WPP_ALL_GLOBAL>
                   : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_LONG> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
-        if (long_dims) smask = B2_WPP_LONG;                  // v and pi in global memory too: 3 CTAs/SM instead of 2
+        if (long_dims) smask = B2_WPP_LONG;                  // v, pi, dv, dpi, cpi, pv in global memory too: 4 CTAs/SM instead of 2
         h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL, true>;
         h->kernel = 2;
     }

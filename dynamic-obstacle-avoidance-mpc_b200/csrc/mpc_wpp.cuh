@@ -44,15 +44,19 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
        PF_WPI, PF_WLAM,                                      // merit-function weights of the SQP line search (SQP kernels only)
        PF_V, PF_PI,                                          // QP iterate v (7 rows) and pi (5): touched by the owner lane and its
                                                              // neighbours k-1 / k+1 only, never inside a sequential sweep
+       PF_DV, PF_DPI, PF_CPI, PF_PV,                         // step dv (7), dpi (5), refinement correction cpi (5), cost-to-go gradient
+                                                             // pv (5): the sweeps only STORE them (z_k, kept in the dpi / cpi rows, is
+                                                             // read by the backward sweep: prefetched one node ahead when in global memory)
        PF_COUNT };
-#define B2_WPP_ALL_SHARED 0x1fffffffu
+#define B2_WPP_ALL_SHARED 0xffffffffffffffffull      // (every placement bit; 33 fields -> 64-bit mask)
 // Placement used by default: EVERY node-private field in global memory.  Measured on B200 (N=20, M=5, 4096 problems,
 // profiles/experiments/r01_hybrid_layout.md): all global, 12 CTAs/SM 11.6 ms; lam,t shared, 7 CTAs/SM 13.1 ms;
 // lam,t,1/t,dlam shared, 5 CTAs/SM 14.3 ms; all shared, 4 CTAs/SM 12.7 ms.
-#define B2_WPP_ALL_GLOBAL ((1u << PF_V) | (1u << PF_PI))   // ... except v and pi (12 rows), which stay in shared memory
-// Long horizons (N = 100: 103 shared rows x 101 nodes = 85 KB, 2 CTAs/SM): v and pi in global memory as well -> 91 rows,
-// 73.8 KB, 3 CTAs/SM.
-#define B2_WPP_LONG 0u
+#define B2_WPP_ALL_GLOBAL ((1ull << PF_V) | (1ull << PF_PI) | (1ull << PF_DV) | (1ull << PF_DPI) | (1ull << PF_CPI) | (1ull << PF_PV))
+                                           // ... except v, pi, dv, dpi, cpi, pv (34 rows), which stay in shared memory
+// Long horizons (N = 100: 103 shared rows x 101 nodes = 85 KB, 2 CTAs/SM): those 34 rows in global memory as well ->
+// 69 rows, 56 KB, 4 CTAs/SM.
+#define B2_WPP_LONG 0ull
 // The six box slots of a node: unrolled by default.  -DB2_WPP_ROLL_BOX walks them with a rolled loop (select chains /
 // predicated adds instead of compile-time register indices; same arithmetic, bit-identical results): 20 KB less code
 // (8104 -> 6936 instructions).  Measured on B200: N=20 +2.0 % at 32 768 problems, -0.2 % at 4096; N=10 -2.5 %; N=100 -10 %
@@ -67,27 +71,31 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 #endif
 
 struct WOff {
-    int sv, hg, rb, lrb, dv, dpi, cv, cpi, lamu, lxu, lxx, pv, lu;             // shared-memory rows read across lanes
+    int sv, hg, rb, lrb, cv, lamu, lxu, lxx, lu;                               // shared-memory rows read across lanes
     int pf[PF_COUNT];                                                           // row of each private field in ITS space
     int total;                                                                  // shared-memory rows (incl. private fields placed there)
     int gtotal;                                                                 // global-memory rows
     __host__ __device__ static int pf_rows(int f, int M, bool sqp)
     {
-        if (f == PF_V) return 7;
-        if (f == PF_PI) return 5;
+        if (f == PF_V || f == PF_DV) return 7;
+        if (f == PF_PI || f == PF_DPI || f == PF_CPI || f == PF_PV) return 5;
         if (f >= PF_WPI) return !sqp ? 0 : f == PF_WPI ? 5 : 12 + 4 * M;
         return f <= PF_DT ? 12 + 4 * M : f == PF_B ? 5 : (f == PF_G || f == PF_RG) ? 7 : f == PF_XU ? 6 : M;
     }
-    __host__ __device__ WOff(int M, unsigned smask, bool sqp)
+    __host__ __device__ WOff(int M, unsigned long long smask, bool sqp)
     {
-        int o = 0;
-        sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5; dv = o; o += 7; dpi = o; o += 5;
-        cv = o; o += 7; cpi = o; o += 5; lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15; pv = o; o += 5; lu = o; o += 2;
-        int g = 0;
-        for (int f = PF_V; f <= PF_PI; f++) {                   // first: their rows are where they have always been
-            if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); }
-            else { pf[f] = g; g += pf_rows(f, M, sqp); }
-        }
+        int o = 0, g = 0;
+        // rows that may live in either space keep their historical place in shared memory
+#define B2_PLACE(f) do { if ((smask >> (f)) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); } else { pf[f] = g; g += pf_rows(f, M, sqp); } } while (0)
+        sv = o; o += 14; hg = o; o += 8; rb = o; o += 5; lrb = o; o += 5;
+        B2_PLACE(PF_DV); B2_PLACE(PF_DPI);
+        cv = o; o += 7;
+        B2_PLACE(PF_CPI);
+        lamu = o; o += 3; lxu = o; o += 10; lxx = o; o += 15;
+        B2_PLACE(PF_PV);
+        lu = o; o += 2;
+        B2_PLACE(PF_V); B2_PLACE(PF_PI);
+#undef B2_PLACE
         for (int f = 0; f < PF_V; f++) {
             if ((smask >> f) & 1u) { pf[f] = o; o += pf_rows(f, M, sqp); }
             else { pf[f] = g; g += pf_rows(f, M, sqp); }
@@ -100,11 +108,11 @@ struct WOff {
 __host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd shared-memory row stride
 __host__ __device__ inline int b2_wpp_gstride(int N) { return N + 1; }               // global rows packed (footprint over sector alignment)
 #define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
-__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned smask, bool sqp = false)
+__host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned long long smask, bool sqp = false)
 {
     return sizeof(double) * ((size_t)WOff(M, smask, sqp).total * b2_wpp_stride(N) + B2_WPP_SCRATCH);
 }
-__host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned smask, bool sqp = false)    // per resident CTA
+__host__ __device__ inline size_t b2_wpp_priv_doubles(int N, int M, unsigned long long smask, bool sqp = false)    // per resident CTA
 {
     return (size_t)WOff(M, smask, sqp).gtotal * b2_wpp_gstride(N);
 }
@@ -142,7 +150,7 @@ __device__ __forceinline__ double b2_bcast(double v, int src) { return __shfl_sy
 // expansion modes
 enum { XP_SOLVE = 0, XP_REFINE = 1, XP_UPDATE = 2, XP_LIN = 3 };
 
-template <int MT, int NT, unsigned SMASK, bool SQP = false>
+template <int MT, int NT, unsigned long long SMASK, bool SQP = false>
 struct WppSolver {
     const B2Params& p;
     const int b, lane, N, NS, GS, M, nct;
@@ -188,6 +196,13 @@ struct WppSolver {
     {
         if ((SMASK >> PF_PI) & 1u) return sm[(o.pf[PF_PI] + i) * NS + kk];
         return gm[(size_t)((o.pf[PF_PI] + i) * GS + kk)];
+    }
+    // row i of placeable field F at node kk
+    template <int F>
+    __device__ __forceinline__ double& R(int i, int kk) const
+    {
+        if ((SMASK >> F) & 1u) return sm[(o.pf[F] + i) * NS + kk];
+        return gm[(size_t)((o.pf[F] + i) * GS + kk)];
     }
     __device__ __forceinline__ bool box_on(int s, int kk) const { return s < 2 ? (kk < N) : (kk > 0 && kk < N); }
     __device__ __forceinline__ double scal(int kk) const { return kk < N ? p.dt : 1.0; }
@@ -241,9 +256,9 @@ struct WppSolver {
             }
             for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; Q<PF_DT>(i) = 0.0; }
 #pragma unroll
-            for (int i = 0; i < 7; i++) S(o.dv + i, k) = 0.0;
+            for (int i = 0; i < 7; i++) R<PF_DV>(i, k) = 0.0;
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(o.dpi + i, k) = 0.0;
+            for (int i = 0; i < 5; i++) R<PF_DPI>(i, k) = 0.0;
 #pragma unroll
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
@@ -326,10 +341,10 @@ struct WppSolver {
     {
         for (k = lane; k <= N; k += 32) {
 #pragma unroll
-            for (int i = 0; i < 7; i++) VV(i, k) += a * S(o.dv + i, k);
+            for (int i = 0; i < 7; i++) VV(i, k) += a * R<PF_DV>(i, k);
             if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) PP(i, k) += a * S(o.dpi + i, k);
+                for (int i = 0; i < 5; i++) PP(i, k) += a * R<PF_DPI>(i, k);
             }
         }
         __syncwarp();
@@ -457,7 +472,7 @@ struct WppSolver {
                 S(o.hg + i, k) = rg[i] + gt[i];
                 S(o.cv + i, k) = Hx[i];
             }
-            S(o.cpi + 0, k) = hxy;
+            S(o.hg + 7, k) = hxy;
         }
         sum = b2_warp_sum(sum);
         nrm[0] = b2_warp_max_nonneg(n0); nrm[1] = b2_warp_max_nonneg(n1); nrm[2] = b2_warp_max_nonneg(n2); nrm[3] = b2_warp_max_nonneg(n3);
@@ -491,7 +506,7 @@ struct WppSolver {
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
             if (mi == mj) m = S(o.cv + mi, kk);                 // condensed node Hessian, left there by head()
-            if (mi == 3 && mj == 2) m = S(o.cpi + 0, kk);
+            if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
             if (kk < N) {
                 // A: AL = [B A]^T Lxx(kk+1)
                 {
@@ -677,14 +692,27 @@ struct WppSolver {
     __device__ void riccati_solve(int kind)
     {
         const bool itr = (kind == 3);
-        const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.dv, oDPI = itr ? o.cpi : o.dpi;
+        // right-hand side rb / lrb and the outputs dv / cv, dpi / cpi.  cv always lives in shared memory (it doubles as the
+        // node Hessian of the factorisation); dv, dpi, cpi, pv may live in global memory (long horizons): the sweeps only
+        // store them, except z_k (kept in the dpi / cpi rows), which the backward sweep then prefetches one node ahead.
+        constexpr bool DVS = (SMASK >> PF_DV) & 1u, DPS = (SMASK >> PF_DPI) & 1u;
+        static_assert(((SMASK >> PF_DPI) & 1u) == ((SMASK >> PF_CPI) & 1u), "dpi and cpi share a placement");
+        const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.pf[PF_DV], oDPI = itr ? o.pf[PF_CPI] : o.pf[PF_DPI];
+        auto rDV = [&](int i, int kk) -> double& {
+            if (DVS || itr) return sm[(oDV + i) * NS + kk];
+            return gm[(size_t)((oDV + i) * GS + kk)];
+        };
+        auto rDPI = [&](int i, int kk) -> double& {
+            if (DPS) return sm[(oDPI + i) * NS + kk];
+            return gm[(size_t)((oDPI + i) * GS + kk)];
+        };
         for (k = lane; k < N; k += 32) {
             double rb[5], z[5];
 #pragma unroll
             for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
             ctg_mul(k + 1, rb, z);
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(oDPI + i, k) = z[i];            // z_k (overwritten by dpi_k below)
+            for (int i = 0; i < 5; i++) rDPI(i, k) = z[i];                // z_k (overwritten by dpi_k below)
         }
         __syncwarp();
         const int c5 = lane < 5 ? lane : 4;
@@ -698,14 +726,23 @@ struct WppSolver {
         double pf[5];
         {
             const double pc = S(o.hg + 2 + c5, N);
-            if (lane < 5) S(o.pv + lane, N) = pc;
+            if (lane < 5) R<PF_PV>(lane, N) = pc;
 #pragma unroll
             for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
         }
-        for (int kk = N - 1; kk >= 0; kk--) {
-            double s[5];
+        double zc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (!DPS) {
 #pragma unroll
-            for (int r = 0; r < 5; r++) s[r] = pf[r] + S(oDPI + r, kk);
+            for (int r = 0; r < 5; r++) zc[r] = rDPI(r, N - 1);
+        }
+        for (int kk = N - 1; kk >= 0; kk--) {
+            double s[5], zn[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (!DPS && kk > 0) {                                           // next node's z: an L2 round trip off the critical chain
+#pragma unroll
+                for (int r = 0; r < 5; r++) zn[r] = rDPI(r, kk - 1);
+            }
+#pragma unroll
+            for (int r = 0; r < 5; r++) s[r] = pf[r] + (DPS ? S(oDPI + r, kk) : zc[r]);
             // short dependency trees: the chain through this loop is the critical path of a solve
             const double w0 = (S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0]) + (S(o.sv + SV_B10, kk) * s[1] + h * s[3]);
             const double w1 = (S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0]) + (S(o.sv + SV_B11, kk) * s[1] + h2 * s[2]) + h * s[4];
@@ -717,15 +754,19 @@ struct WppSolver {
                 const double pa = (S(o.hg + 2 + c5, kk) + S(acol[0], kk) * s[0]) + (S(acol[1], kk) * s[1] + S(acol[2], kk) * s[2]);
                 const double pb = S(acol[3], kk) * s[3] + S(acol[4], kk) * s[4];
                 const double pc = (pa + pb) - (S(o.lxu + 2 * c5, kk) * lu0 + S(o.lxu + 2 * c5 + 1, kk) * lu1);
-                if (lane < 5) S(o.pv + lane, kk) = pc;
+                if (lane < 5) R<PF_PV>(lane, kk) = pc;
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
+            }
+            if (!DPS) {
+#pragma unroll
+                for (int r = 0; r < 5; r++) zc[r] = zn[r];
             }
         }
         __syncwarp();
         // ---- forward
         double dx[5] = {0, 0, 0, 0, 0};
-        if (lane < 5) S(oDV + 2 + lane, 0) = 0.0;
+        if (lane < 5) rDV(2 + lane, 0) = 0.0;
         for (int kk = 0; kk < N; kk++) {
             double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
             if (kk > 0) {
@@ -737,20 +778,20 @@ struct WppSolver {
             const double du0 = (-r0 - l10 * du1) * l00i;
             const double xa = (S(oRB + c5, kk) + S(arow[2], kk) * dx[0] + S(arow[3], kk) * dx[1]) + (S(arow[4], kk) * dx[2] + S(arow[5], kk) * dx[3] + S(arow[6], kk) * dx[4]);
             const double xn = xa + (S(arow[0], kk) * du0 + S(arow[1], kk) * du1);
-            if (lane == 0) { S(oDV + 0, kk) = du0; S(oDV + 1, kk) = du1; }
-            if (lane < 5) S(oDV + 2 + lane, kk + 1) = xn;
+            if (lane == 0) { rDV(0, kk) = du0; rDV(1, kk) = du1; }
+            if (lane < 5) rDV(2 + lane, kk + 1) = xn;
 #pragma unroll
             for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
         }
-        if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
+        if (lane == 0) { rDV(0, N) = 0.0; rDV(1, N) = 0.0; }
         __syncwarp();
         for (k = lane; k < N; k += 32) {
             double dxn[5], y[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
+            for (int i = 0; i < 5; i++) dxn[i] = rDV(2 + i, k + 1);
             ctg_mul(k + 1, dxn, y);
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(oDPI + i, k) = y[i] + S(o.pv + i, k + 1);
+            for (int i = 0; i < 5; i++) rDPI(i, k) = y[i] + R<PF_PV>(i, k + 1);
         }
         __syncwarp();
     }
@@ -773,13 +814,13 @@ struct WppSolver {
 #pragma unroll
         for (int i = 0; i < 7; i++) {
             v[i] = VV(i, k);
-            dv[i] = S(o.dv + i, k);
+            dv[i] = R<PF_DV>(i, k);
             cv[i] = 0.0;
-            if (MODE == XP_REFINE) { cv[i] = S(o.cv + i, k); dv[i] += cv[i]; S(o.dv + i, k) = dv[i]; }
+            if (MODE == XP_REFINE) { cv[i] = S(o.cv + i, k); dv[i] += cv[i]; R<PF_DV>(i, k) = dv[i]; }
         }
         if (MODE == XP_REFINE && k < N) {
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(o.dpi + i, k) += S(o.cpi + i, k);
+            for (int i = 0; i < 5; i++) R<PF_DPI>(i, k) += R<PF_CPI>(i, k);
         }
         B2_BOX_LOOP
         for (int s = 0; s < 6; s++) {
@@ -930,21 +971,21 @@ struct WppSolver {
             const double* Hd = k < N ? p.Hd : p.Hde;
             double dv[7], lrg[7];
 #pragma unroll
-            for (int i = 0; i < 7; i++) { dv[i] = S(o.dv + i, k); lrg[i] = Q<PF_RG>(i) + Hd[i] * dv[i]; }
+            for (int i = 0; i < 7; i++) { dv[i] = R<PF_DV>(i, k); lrg[i] = Q<PF_RG>(i) + Hd[i] * dv[i]; }
             double sv[10];
             if (k < N) {
 #pragma unroll
                 for (int i = 0; i < 10; i++) sv[i] = S(o.sv + i, k);
                 double dp[5], bt[7];
 #pragma unroll
-                for (int i = 0; i < 5; i++) dp[i] = S(o.dpi + i, k);
+                for (int i = 0; i < 5; i++) dp[i] = R<PF_DPI>(i, k);
                 b2_bat_mul(sv, p.dt, p.dt2h, dp, bt);
 #pragma unroll
                 for (int i = 0; i < 7; i++) lrg[i] += bt[i];
             }
             if (k > 0) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) lrg[2 + i] -= S(o.dpi + i, k - 1);
+                for (int i = 0; i < 5; i++) lrg[2 + i] -= R<PF_DPI>(i, k - 1);
             }
             double ap = 0, ad = 0, s1 = 0, s2 = 0;
             expand<XP_LIN>(0, 0.0, 0.0, ap, ad, s1, s2, lrg, ln0);
@@ -953,7 +994,7 @@ struct WppSolver {
                 b2_ba_mul(sv, p.dt, p.dt2h, dv, lrb);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
-                    lrb[i] += S(o.rb + i, k) - S(o.dv + 2 + i, k + 1);
+                    lrb[i] += S(o.rb + i, k) - R<PF_DV>(2 + i, k + 1);
                     S(o.lrb + i, k) = lrb[i];
                     ln1 = fmax(ln1, fabs(lrb[i]));
                 }
@@ -1255,7 +1296,7 @@ struct WppSolver {
 #else
 #define B2_WPP_BOUNDS(NT, SMASK) __launch_bounds__(32, (NT > 0 && NT < 32 && SMASK != B2_WPP_ALL_SHARED) ? B2_WPP_MINB : 1)
 #endif
-template <int MT, int NT, unsigned SMASK, bool SQP = false>
+template <int MT, int NT, unsigned long long SMASK, bool SQP = false>
 __global__ void B2_WPP_BOUNDS(NT, SMASK) b2_rti_solve_wpp(const B2Params p)
 {
     extern __shared__ double b2_smem[];
