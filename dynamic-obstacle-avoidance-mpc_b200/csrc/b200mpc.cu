@@ -809,12 +809,22 @@ extern "C" int b2mpc_solve_host(b2mpc* h, int64_t batch, const double* x0, const
     if ((rc = b2mpc_set_host(h, B2MPC_SL, sl, batch, stream))) return rc;
     if ((rc = b2mpc_set_host(h, B2MPC_SU, su, batch, stream))) return rc;
     if ((rc = b2mpc_solve(h, batch, stream))) return rc;
-    if ((rc = b2mpc_get_host(h, B2MPC_X, x, batch, stream))) return rc;
-    if ((rc = b2mpc_get_host(h, B2MPC_U, u, batch, stream))) return rc;
-    if ((rc = b2mpc_get_host(h, B2MPC_SL, sl, batch, stream))) return rc;
-    if ((rc = b2mpc_get_host(h, B2MPC_SU, su, batch, stream))) return rc;
-    if (status && (rc = b2mpc_get_i32_host(h, B2MPC_STATUS, status, batch, stream))) return rc;
-    if (qp_iter && (rc = b2mpc_get_i32_host(h, B2MPC_QP_ITER, qp_iter, batch, stream))) return rc;
+    // results: the four iterate fields are transposed into disjoint parts of the staging buffer (it holds the largest
+    // field, (N+1)(12+4M) doubles per problem, more than x+u+sl+su together) and copied back with ONE synchronisation
+    cudaStream_t st = (cudaStream_t)stream;
+    const int fields[4] = {B2MPC_X, B2MPC_U, B2MPC_SL, B2MPC_SU};
+    double* const dst[4] = {x, u, sl, su};
+    size_t off = 0;
+    for (int i = 0; i < 4; i++) {
+        const size_t n = (size_t)h->len[fields[i]] * batch;
+        if (off + n > h->stage_elems) return fail(B2MPC_EINVAL, "staging buffer too small");
+        if ((rc = b2mpc_get(h, fields[i], h->stage_d + off, batch, B2MPC_LAYOUT_AOS, stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(dst[i], h->stage_d + off, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        off += n;
+    }
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, h->fi[B2MPC_STATUS], sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    if (qp_iter) CUDA_TRY(cudaMemcpyAsync(qp_iter, h->fi[B2MPC_QP_ITER], sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return B2MPC_OK;
 }
 
