@@ -250,6 +250,37 @@ def main():
     # device result of the host path equals the device path
     assert np.array_equal(host_it["u"], solver.get("u", B).cpu().numpy())
 
+    # ---------------- steady state: the same solve on WARM iterates ----------------
+    # 50 closed-loop control steps on device (obstacle prediction, slack weights, solve, plant/obstacle step, shift:
+    # robot_ocp_problem.py:184-260), then the solve of control step 51 is timed like the cold one
+    K_WARM = 50
+    solver.set("x0", dev_t["x0"]); solver.set("obst", torch.from_numpy(sc["obst"]).to(dev)); solver.set("goal", torch.from_numpy(sc["goal"]).to(dev))
+    solver.set("yref", dev_t["yref"])
+    restore(); solver.loop_reset(B)
+    for _ in range(K_WARM):
+        solver.obst_predict(B); solver.prepare_slack(B); solver.solve(B)
+        solver.loop_post(B, None, False, True, world.TOL)
+    solver.obst_predict(B); solver.prepare_slack(B)
+    warm = {k: solver.get(k, B).clone() for k in names_it}
+
+    def step_warm():
+        for k in names_it:
+            solver.set(k, warm[k])
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream); solver.solve(B); e1.record(stream)
+        return e0, e1
+
+    for _ in range(2):
+        step_warm()
+    torch.cuda.synchronize(dev)
+    if world_size > 1:
+        dist.barrier()
+    wevs = [step_warm() for _ in range(a.steps)]
+    torch.cuda.synchronize(dev)
+    warm_ms = float(np.sum([e0.elapsed_time(e1) for e0, e1 in wevs]))
+    warm_it = float(solver.get_int("qp_iter", B).sum().item())
+
     # ---------------- p50 latency of ONE problem (the reference's one-at-a-time use) ----------------
     lat1 = None
     if rank == 0:
@@ -269,8 +300,8 @@ def main():
         s1.close()
 
     # ---------------- reduce over ranks (max time; sum of work) ----------------
-    sums, maxs = sharding.reduce_stats({"B": B, "qp_iter": float(qp_iter.sum()), "fail": float((status != 0).sum())},
-                                       {"total_ms": total_ms, "e2e_s": e2e_s}, device=dev)
+    sums, maxs = sharding.reduce_stats({"B": B, "qp_iter": float(qp_iter.sum()), "fail": float((status != 0).sum()), "warm_it": warm_it},
+                                       {"total_ms": total_ms, "e2e_s": e2e_s, "warm_ms": warm_ms}, device=dev)
     total_ms_max, e2e_s_max = maxs["total_ms"], maxs["e2e_s"]
     tot_B, tot_it, tot_fail = sums["B"], sums["qp_iter"], sums["fail"]
 
@@ -305,6 +336,10 @@ def main():
                        "parallelism": f"env-sharded x{world_size}, no data-path collective"},
             "p50_latency_ms_per_batch": float(np.median(step_ms)), "p50_latency_ms_single_problem": lat1,
             "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),
+            "steady_state": {"value": tot_B * a.steps / (maxs["warm_ms"] * 1e-3), "unit": UNIT, "ms_per_step": maxs["warm_ms"] / a.steps,
+                             "mean_qp_iter": sums["warm_it"] / tot_B,
+                             "what": f"the same solve on warm iterates: control step {K_WARM + 1} of the on-device closed loop "
+                                     "(shifted previous solution), device-resident inputs"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "peak_source": "self-measured register-resident DFMA chains (b2mpc_dfma_peak); "
