@@ -70,3 +70,23 @@ def test_missing_library_is_a_loud_error(tmp_path, monkeypatch):
     monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(capi.B2mpcError):
         capi.lib()
+
+
+def test_ctypes_config_layout_matches_the_header(tmp_path):
+    """the ctypes mirror of b2mpc_config (b200mpc/capi.py) against what a C compiler makes of include/b200mpc.h"""
+    import subprocess
+    names = [n for n, _ in capi.Config._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200mpc.h"\nint main(void){printf("%zu\\n", sizeof(b2mpc_config));\n' +
+                   "".join(f'printf("%zu\\n", offsetof(b2mpc_config, {n}));\n' for n in names) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(capi.Config)
+    for n, off in zip(names, out[1:]):
+        assert getattr(capi.Config, n).offset == off, n
+    # and the field / status enumerations
+    hdr = open(os.path.join(ROOT, "include", "b200mpc.h")).read()
+    for name, val in (("B2MPC_NLP_RES", capi.NLP_RES), ("B2MPC_N_FIELDS", capi.NLP_RES + 1), ("B2MPC_SQP_ITER", capi.SQP_ITER),
+                      ("B2MPC_N_IFIELDS", capi.SQP_ITER + 1), ("B2MPC_U0", capi.U0), ("B2MPC_STATS", capi.STATS)):
+        assert re.search(rf"\b{name}\s*=\s*{val}\b", hdr), name
