@@ -66,6 +66,13 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 #else
 #define B2_BOX_LOOP _Pragma("unroll")
 #endif
+// B2_WPP_NO_DT: the slack steps dt are not stored (one row per constraint) but recomputed by head() from dv, ds and the
+// residual of the OLD iterate -- the very expression expand() evaluated: 12 % fewer node-private rows, 4 stores per obstacle
+// and solve less.  Measured on B200: N=20 9.89 -> 9.58 ms per 4096 problems, 67.0 -> 64.7 ms per 32 768 (507 k solves/s);
+// N=100 / M=20 284 -> 271 ms; identical iteration counts.  -DB2_WPP_NO_DT=0 restores the stored rows.
+#ifndef B2_WPP_NO_DT
+#define B2_WPP_NO_DT 1
+#endif
 #ifndef B2_WPP_MINB
 #define B2_WPP_MINB 12          // resident CTAs per SM the N=20 layout is compiled for (register cap 65536/32/MINB = 170)
 #endif
@@ -77,6 +84,7 @@ struct WOff {
     int gtotal;                                                                 // global-memory rows
     __host__ __device__ static int pf_rows(int f, int M, bool sqp)
     {
+        if (f == PF_DT && B2_WPP_NO_DT) return 0;
         if (f == PF_V || f == PF_DV) return 7;
         if (f == PF_PI || f == PF_DPI || f == PF_CPI || f == PF_PV) return 5;
         if (f >= PF_WPI) return !sqp ? 0 : f == PF_WPI ? 5 : 12 + 4 * M;
@@ -254,7 +262,7 @@ struct WppSolver {
 #pragma unroll
                 for (int i = 0; i < 5; i++) v[2 + i] = p.X0[(size_t)i * Bm + b] - xk[i];
             }
-            for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; Q<PF_DT>(i) = 0.0; }
+            for (int i = 0; i < nct; i++) { Q<PF_LAM>(i) = 0.0; Q<PF_T>(i) = 0.0; Q<PF_TINV>(i) = 0.0; Q<PF_DD>(i) = 0.0; if (!B2_WPP_NO_DT) Q<PF_DT>(i) = 0.0; }
 #pragma unroll
             for (int i = 0; i < 7; i++) R<PF_DV>(i, k) = 0.0;
 #pragma unroll
@@ -341,7 +349,11 @@ struct WppSolver {
     {
         for (k = lane; k <= N; k += 32) {
 #pragma unroll
-            for (int i = 0; i < 7; i++) VV(i, k) += a * R<PF_DV>(i, k);
+            for (int i = 0; i < 7; i++) {
+                const double vo = VV(i, k);
+                if (B2_WPP_NO_DT) S(o.cv + i, k) = vo;          // the old iterate, for the recomputation of dt below (cv is free here)
+                VV(i, k) = vo + a * R<PF_DV>(i, k);
+            }
             if (k < N) {
 #pragma unroll
                 for (int i = 0; i < 5; i++) PP(i, k) += a * R<PF_DPI>(i, k);
@@ -375,15 +387,23 @@ struct WppSolver {
                 if (!box_on(s, k)) continue;
                 const int il = o_lb + s, iu = o_ub + s;
                 double ll = Q<PF_LAM>(il) + a * Q<PF_DD>(il), lu_ = Q<PF_LAM>(iu) + a * Q<PF_DD>(iu);
-                double tl = Q<PF_T>(il) + a * Q<PF_DT>(il), tu = Q<PF_T>(iu) + a * Q<PF_DT>(iu);
+                double lb, ub;
+                box_bounds(s, lb, ub);
+                double tl, tu;
+                if (B2_WPP_NO_DT) {
+                    const double tlo = Q<PF_T>(il), tuo = Q<PF_T>(iu);
+                    const double vos = S(o.cv + b2_slot2v(s), k), dvs = R<PF_DV>(b2_slot2v(s), k);
+                    const double dtl = dvs + ((vos - lb) - tlo), dtu = -dvs + ((ub - vos) - tuo);      // = expand()'s dtl, dtu
+                    tl = tlo + a * dtl; tu = tuo + a * dtu;
+                } else {
+                    tl = Q<PF_T>(il) + a * Q<PF_DT>(il); tu = Q<PF_T>(iu) + a * Q<PF_DT>(iu);
+                }
                 if (ll <= p.lam_min) ll = p.lam_min;
                 if (lu_ <= p.lam_min) lu_ = p.lam_min;
                 if (tl <= p.t_min) tl = p.t_min;
                 if (tu <= p.t_min) tu = p.t_min;
                 Q<PF_LAM>(il) = ll; Q<PF_LAM>(iu) = lu_; Q<PF_T>(il) = tl; Q<PF_T>(iu) = tu;
                 slot_add(rg, s, -ll + lu_);
-                double lb, ub;
-                box_bounds(s, lb, ub);
                 const double vv = slot_get(v, s);
                 const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
                 n2 = fmax(n2, fmax(fabs(rdl), fabs(rdu)));
@@ -397,13 +417,31 @@ struct WppSolver {
                 slot_add(gt, s, (ml + ll * rdl) * til - (mu_ + lu_ * rdu) * tiu);
             }
             const double Zuq = sc * p.Zu;
+            double vo2 = 0.0, vo3 = 0.0, dv2 = 0.0, dv3 = 0.0;
+            if (B2_WPP_NO_DT) { vo2 = S(o.cv + 2, k); vo3 = S(o.cv + 3, k); dv2 = R<PF_DV>(2, k); dv3 = R<PF_DV>(3, k); }
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
                 const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
                 double l0 = Q<PF_LAM>(i0) + a * Q<PF_DD>(i0), l1 = Q<PF_LAM>(i1) + a * Q<PF_DD>(i1);
                 double l2 = Q<PF_LAM>(i2) + a * Q<PF_DD>(i2), l3 = Q<PF_LAM>(i3) + a * Q<PF_DD>(i3);
-                double t0 = Q<PF_T>(i0) + a * Q<PF_DT>(i0), t1 = Q<PF_T>(i1) + a * Q<PF_DT>(i1);
-                double t2 = Q<PF_T>(i2) + a * Q<PF_DT>(i2), t3 = Q<PF_T>(i3) + a * Q<PF_DT>(i3);
+                double t0, t1, t2, t3;
+                if (B2_WPP_NO_DT) {
+                    // dt of the stored step, recomputed the way expand() computed it (old v, old slacks, old t)
+                    const double cxo = Q<PF_CX>(j), cyo = Q<PF_CY>(j);
+                    const double cdv = cxo * dv2 + cyo * dv3;
+                    const double cvalo = cxo * vo2 + cyo * vo3;
+                    const double t0o = Q<PF_T>(i0), t1o = Q<PF_T>(i1), t2o = Q<PF_T>(i2), t3o = Q<PF_T>(i3);
+                    const double slo = Q<PF_SL>(j), suo = Q<PF_SU>(j), dslo = Q<PF_DSL>(j), dsuo = Q<PF_DSU>(j);
+                    const double rd0o = cvalo + slo - Q<PF_LG>(j) - t0o;
+                    const double rd1o = Q<PF_UG>(j) - cvalo + suo - t1o;
+                    const double rd2o = slo + Q<PF_SLI>(j) - t2o;
+                    const double rd3o = suo + Q<PF_SUI>(j) - t3o;
+                    const double dt0 = cdv + dslo + rd0o, dt1 = -cdv + dsuo + rd1o, dt2 = dslo + rd2o, dt3 = dsuo + rd3o;
+                    t0 = t0o + a * dt0; t1 = t1o + a * dt1; t2 = t2o + a * dt2; t3 = t3o + a * dt3;
+                } else {
+                    t0 = Q<PF_T>(i0) + a * Q<PF_DT>(i0); t1 = Q<PF_T>(i1) + a * Q<PF_DT>(i1);
+                    t2 = Q<PF_T>(i2) + a * Q<PF_DT>(i2); t3 = Q<PF_T>(i3) + a * Q<PF_DT>(i3);
+                }
                 if (l0 <= p.lam_min) l0 = p.lam_min;
                 if (l1 <= p.lam_min) l1 = p.lam_min;
                 if (l2 <= p.lam_min) l2 = p.lam_min;
@@ -838,13 +876,13 @@ struct WppSolver {
                 dlu = -(rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * dtu) * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = keep_dd ? dtl * dll : dll;
                 Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
-                Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
+                if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else if (MODE == XP_REFINE) {
                 const double cvv = slot_get(cv, s);
                 dll = Q<PF_DD>(il) - ll * cvv * Q<PF_TINV>(il);
                 dlu = Q<PF_DD>(iu) + lu_ * cvv * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
-                Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu;
+                if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else {
                 dll = Q<PF_DD>(il); dlu = Q<PF_DD>(iu);
             }
@@ -897,7 +935,7 @@ struct WppSolver {
                 dl0 = Q<PF_DD>(i0); dl1 = Q<PF_DD>(i1); dl2 = Q<PF_DD>(i2); dl3 = Q<PF_DD>(i3);
             }
             const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
-            if (MODE == XP_SOLVE || MODE == XP_REFINE) { Q<PF_DT>(i0) = dt0; Q<PF_DT>(i1) = dt1; Q<PF_DT>(i2) = dt2; Q<PF_DT>(i3) = dt3; }
+            if (!B2_WPP_NO_DT && (MODE == XP_SOLVE || MODE == XP_REFINE)) { Q<PF_DT>(i0) = dt0; Q<PF_DT>(i1) = dt1; Q<PF_DT>(i2) = dt2; Q<PF_DT>(i3) = dt3; }
             consume<MODE>(i0, l0, t0, dt0, dl0, a, ap, ad, s1, s2);
             consume<MODE>(i1, l1, t1, dt1, dl1, a, ap, ad, s1, s2);
             consume<MODE>(i2, l2, t2, dt2, dl2, a, ap, ad, s1, s2);
