@@ -910,7 +910,7 @@ struct WppSolver {
                 slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
                 dsl = -(l0 * ti0 * cdv + rhol) * Q<PF_DLI>(j);
                 dsu = -(-l1 * ti1 * cdv + rhou) * Q<PF_DUI>(j);
-                Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu;
+                if (!keep_dd) { Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu; }      // (the predictor's slack steps are never read)
                 const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
                 dl0 = -(rm_of(kind, l0, t0, Q<PF_DD>(i0), smu) + l0 * dt0) * ti0;
                 dl1 = -(rm_of(kind, l1, t1, Q<PF_DD>(i1), smu) + l1 * dt1) * ti1;
