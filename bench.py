@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--n-obst", type=int, default=5)
     ap.add_argument("--tf", type=float, default=2.0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 thread-per-problem, 2 warp-per-problem")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 2 warp-per-problem (node-private rows in global memory), 3 warp-per-problem all-shared")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (0 = auto)")
     return ap.parse_args()

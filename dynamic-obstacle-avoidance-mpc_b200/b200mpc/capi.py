@@ -94,7 +94,7 @@ def lib():
         if name not in ("b2mpc_last_error", "b2mpc_default_config", "b2mpc_field_len", "b2mpc_workspace_bytes",
                         "b2mpc_launch_count", "b2mpc_field_ptr"):
             fn.restype = C.c_int
-    if L.b2mpc_abi_version() != 2:
+    if L.b2mpc_abi_version() != 3:
         raise B2mpcError("libb200mpc ABI version mismatch")
     _lib = L
     return L

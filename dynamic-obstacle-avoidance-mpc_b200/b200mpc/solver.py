@@ -171,8 +171,13 @@ class BatchedMpcSolver:
         return status, qp_iter
 
     @property
+    def kernel_id(self):
+        """2 = warp-per-problem with the node-private rows in global memory (persistent grid), 3 = everything in shared memory"""
+        return capi.lib().b2mpc_kernel(self._h)
+
+    @property
     def kernel_name(self):
-        return {1: "thread-per-problem", 2: "warp-per-problem", 3: "warp-per-problem (all shared)"}[capi.lib().b2mpc_kernel(self._h)]
+        return {2: "warp-per-problem", 3: "warp-per-problem (all shared)"}[self.kernel_id]
 
     @property
     def launch_count(self):

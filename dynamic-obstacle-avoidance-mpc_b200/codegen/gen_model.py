@@ -149,7 +149,7 @@ class Emitter:
             L.append(f"    const double {sym} = {ccode(ex)};")
         for (ang, _, sn, cs), ex in zip(pre, red_ang):
             L.append(f"    double {sn}, {cs};")
-            L.append(f"    sincos({ccode(ex)}, &{sn}, &{cs});")
+            L.append(f"    MODEL_SINCOS({ccode(ex)}, &{sn}, &{cs});")
         for sym, ex in late:
             L.append(f"    const double {sym} = {ccode(ex)};")
         nx = len(xn)
@@ -226,6 +226,11 @@ def main():
     L.append("// DO NOT EDIT BY HAND -- regenerate with `python codegen/gen_model.py`.")
     L.append("#pragma once")
     L.append("#include <math.h>")
+    L.append("/* sin/cos of the heading: csrc/b2_math.cuh defines the same operation sequence for the GPU and the CPU mirror */")
+    L.append('#include "b2_math.cuh"')
+    L.append("#ifndef MODEL_SINCOS")
+    L.append("#define MODEL_SINCOS(x, s, c) b2_sincos((x), (s), (c))")
+    L.append("#endif")
     L.append(f"#define MODEL_NX {nx}")
     L.append(f"#define MODEL_NU {nu}")
     L.append(f"#define MODEL_N_OBST_DEFAULT {len(p) // 2}   /* world_specification.py:25 */")

@@ -12,7 +12,7 @@
 
 #include "../../include/b200mpc.h"
 #include "mpc_common.cuh"
-#include "mpc_tpp.cuh"
+#include "mpc_params.h"
 #include "mpc_wpp.cuh"
 
 static thread_local std::string g_err;
@@ -40,8 +40,6 @@ struct b2mpc {
     int64_t len[B2MPC_N_FIELDS];
     double* f[B2MPC_N_FIELDS];       // SoA [len][Bm]
     int32_t* fi[B2MPC_N_IFIELDS];    // [Bm]
-    double* ws;
-    size_t ws_bytes;
     double* stage_d;                 // device staging for layout conversion (max field len * Bm)
     double* stage_h;                 // pinned host staging
     int32_t* stage_hi;
@@ -96,39 +94,13 @@ extern "C" void b2mpc_default_config(b2mpc_config* c, int32_t N, int32_t n_obst,
 
 static void fill_params(b2mpc* h)
 {
-    const b2mpc_config& c = h->cfg;
     B2Params& p = h->prm;
-    memset(&p, 0, sizeof(p));
-    p.N = h->N; p.M = h->M; p.Bm = h->Bm; p.B = 0;
-    p.integrator = c.integrator; p.qp_iter_max = c.qp_iter_max;
-    p.pred_corr = c.pred_corr; p.cond_pred_corr = c.cond_pred_corr; p.itref_corr_max = c.itref_corr_max;
-    p.nct = h->nct;
-    p.nlp_iter_max = c.nlp_iter_max; p.nlp_globalization = c.nlp_globalization;
-    for (int i = 0; i < 4; i++) p.nlp_tol[i] = c.nlp_tol[i];
-    p.ls_alpha_min = c.ls_alpha_min; p.ls_alpha_red = c.ls_alpha_reduction; p.ls_eps = c.ls_eps;
-    p.slots_per_stage = B2Off(h->M).total;
-    p.dt = c.tf / c.N; p.dt2h = 0.5 * p.dt * p.dt;
-    const double lm_s = c.lm_scaled_by_dt ? p.dt * c.lm : c.lm;   // acados-version dependent
-    // v order [u_a,u_alpha,x,y,psi,v,omega]; y order [x,y,v,omega,u_a,u_alpha]; stage cost scaled by dt
-    const double Wv[7] = {c.W[4], c.W[5], c.W[0], c.W[1], 0.0, c.W[2], c.W[3]};
-    const double Wev[7] = {0.0, 0.0, c.W_e[0], c.W_e[1], 0.0, c.W_e[2], c.W_e[3]};
-    for (int i = 0; i < 7; i++) {
-        p.Hd[i] = p.dt * Wv[i] + lm_s; p.Wg[i] = p.dt * Wv[i];
-        p.Hde[i] = i < 2 ? 0.0 : Wev[i] + c.lm; p.Wge[i] = Wev[i];
-    }
-    for (int i = 0; i < 4; i++) { p.lbx[i] = c.lbx[i]; p.ubx[i] = c.ubx[i]; }
-    for (int i = 0; i < 2; i++) { p.lbu[i] = c.lbu[i]; p.ubu[i] = c.ubu[i]; }
-    for (int i = 0; i < 6; i++) { p.lb6[i] = i < 2 ? c.lbu[i] : c.lbx[i - 2]; p.ub6[i] = i < 2 ? c.ubu[i] : c.ubx[i - 2]; }
-    p.r2 = c.r2; p.lh = c.lh; p.uh = c.uh; p.zu = c.zu; p.Zu = c.Zu;
-    p.mu0 = c.mu0; p.alpha_min = c.alpha_min; p.res_g_max = c.res_g_max; p.res_b_max = c.res_b_max;
-    p.res_d_max = c.res_d_max; p.res_m_max = c.res_m_max; p.reg_prim = c.reg_prim;
-    p.lam_min = c.lam_min; p.t_min = c.t_min; p.tau_min = c.tau_min; p.thr0 = c.thr0;
+    b2_params_from_config(h->cfg, h->Bm, p);          // everything that is not a pointer (shared with the CPU mirror build)
     p.X0 = h->f[B2MPC_X0]; p.P = h->f[B2MPC_P]; p.YREF = h->f[B2MPC_YREF]; p.ZL = h->f[B2MPC_ZL]; p.ZZL = h->f[B2MPC_ZZL];
     p.X = h->f[B2MPC_X]; p.U = h->f[B2MPC_U]; p.SL = h->f[B2MPC_SL]; p.SU = h->f[B2MPC_SU];
     p.PI = h->f[B2MPC_PI]; p.LAM = h->f[B2MPC_LAM]; p.T = h->f[B2MPC_T]; p.STATS = h->f[B2MPC_STATS];
     p.STATUS = h->fi[B2MPC_STATUS]; p.QP_ITER = h->fi[B2MPC_QP_ITER]; p.QP_STATUS = h->fi[B2MPC_QP_STATUS];
     p.NLP_RES = h->f[B2MPC_NLP_RES]; p.SQP_ITER = h->fi[B2MPC_SQP_ITER];
-    p.WS = h->ws;
 }
 
 extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
@@ -143,7 +115,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     if (cfg->qp_iter_max < 1) return fail(B2MPC_EINVAL, "qp_iter_max must be >= 1");
     if (cfg->nlp_solver != 0 && cfg->nlp_solver != 1) return fail(B2MPC_EINVAL, "nlp_solver must be 0 (SQP_RTI) or 1 (SQP)");
     if (cfg->nlp_solver == 1 && cfg->nlp_iter_max < 1) return fail(B2MPC_EINVAL, "nlp_iter_max must be >= 1");
-    if (cfg->nlp_solver == 1 && cfg->kernel == 1) return fail(B2MPC_EINVAL, "the SQP loop needs a warp-per-problem kernel (kernel 0, 2 or 3)");
+    if (cfg->kernel == 1) return fail(B2MPC_EINVAL, "kernel 1 (the thread-per-problem cross-check) was removed in ABI 3: the cross-check is the CPU mirror build under oracle/simt/");
     if (cfg->nlp_globalization != 0 && cfg->nlp_globalization != 1) return fail(B2MPC_EINVAL, "nlp_globalization must be 0 (FIXED_STEP) or 1 (MERIT_BACKTRACKING)");
     if (cfg->nlp_globalization == 1 && !(cfg->ls_alpha_min > 0.0 && cfg->ls_alpha_min <= 1.0 && cfg->ls_alpha_reduction > 0.0 && cfg->ls_alpha_reduction < 1.0))
         return fail(B2MPC_EINVAL, "line search needs 0 < ls_alpha_min <= 1 and 0 < ls_alpha_reduction < 1");
@@ -201,8 +173,6 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED>;
         h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_SHARED, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_SHARED, true>;
         h->kernel = 3;
-    } else if (cfg->kernel == 1) {
-        h->kernel = 1;
     } else {
         h->wpp_fn = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL>
                   : ref_dims_short ? b2_rti_solve_wpp<5, 10, B2_WPP_ALL_GLOBAL>
@@ -211,14 +181,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL, true>;
         h->kernel = 2;
     }
-    // global scratch of the thread-per-problem kernel
-    h->ws_bytes = h->kernel == 1 ? sizeof(double) * (size_t)B2Off(M).total * (N + 1) * h->Bm : 0;
-    if (h->ws_bytes) {
-        if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(workspace, %zu B) failed", h->ws_bytes); }
-        cudaMemset(h->ws, 0, h->ws_bytes);
-    }
-    h->prm.WS = h->ws;
-    if (h->kernel != 1) {
+    {
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
         h->wpp_smem_sqp = b2_wpp_smem_bytes(N, M, smask_sqp, true);
         if (h->wpp_smem_sqp > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
@@ -283,7 +246,6 @@ extern "C" int b2mpc_destroy(b2mpc* h)
     cudaSetDevice(h->cfg.device);
     for (int i = 0; i < B2MPC_N_FIELDS; i++) if (h->f[i]) cudaFree(h->f[i]);
     for (int i = 0; i < B2MPC_N_IFIELDS; i++) if (h->fi[i]) cudaFree(h->fi[i]);
-    if (h->ws) cudaFree(h->ws);
     if (h->wpriv) cudaFree(h->wpriv);
     if (h->order) cudaFree(h->order);
     if (h->stage_d) cudaFree(h->stage_d);
@@ -298,7 +260,7 @@ extern "C" int64_t b2mpc_field_len(const b2mpc* h, int field)
     if (!h || field < 0 || field >= B2MPC_N_FIELDS) return -1;
     return h->len[field];
 }
-extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)(h->ws_bytes + h->wpriv_bytes) : -1; }
+extern "C" int64_t b2mpc_workspace_bytes(const b2mpc* h) { return h ? (int64_t)h->wpriv_bytes : -1; }
 extern "C" int64_t b2mpc_launch_count(const b2mpc* h) { return h ? h->launches : -1; }
 extern "C" int b2mpc_kernel(const b2mpc* h) { return h ? h->kernel : -1; }
 extern "C" double* b2mpc_field_ptr(b2mpc* h, int field)
@@ -728,7 +690,6 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
-    if (sqp && h->kernel == 1) return fail(B2MPC_EINVAL, "the SQP loop needs a warp-per-problem kernel (kernel 0, 2 or 3)");
     cudaStream_t st = (cudaStream_t)stream;
     B2Params p = h->prm;
     p.B = (int)batch;
@@ -736,7 +697,7 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
         if (max_iter > 0) p.nlp_iter_max = max_iter;
         if (tol4) for (int i = 0; i < 4; i++) p.nlp_tol[i] = tol4[i];
     }
-    if (h->kernel != 1) {
+    {
         // order buffer: [order (Bm) | key (Bm) | hist (MAXKEYS) | fill (MAXKEYS) | work counter]
         int32_t* key = h->order + h->Bm;
         int32_t* hist = key + h->Bm;
@@ -772,11 +733,6 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
             } else
             h->wpp_fn<<<blocks, 32, h->wpp_smem, st>>>(p);
         }
-    } else {
-        const int threads = 64;
-        const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
-        if (h->M == 5) b2_rti_solve_tpp<5><<<blocks, threads, 0, st>>>(p);
-        else b2_rti_solve_tpp<0><<<blocks, threads, 0, st>>>(p);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -9,6 +9,13 @@
 #include <stdint.h>
 #include "model_generated.cuh"
 
+// dynamic shared memory of a kernel (the CPU SIMT emulator under oracle/simt/ hands out a per-block buffer instead)
+#ifdef SIMT_EMU
+#define B2_DYNAMIC_SMEM(type, name) SIMT_DYNAMIC_SMEM(type, name)
+#else
+#define B2_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 #define B2_NX 5
 #define B2_NU 2
 #define B2_NV 7
@@ -49,7 +56,6 @@ struct B2Params {
     int32_t nlp_globalization;   // 0 FIXED_STEP, 1 MERIT_BACKTRACKING
     double nlp_tol[4];
     double ls_alpha_min, ls_alpha_red, ls_eps;
-    int32_t slots_per_stage;
     double dt, dt2h;             // h, h*h/2
     double Hd[7], Hde[7];        // Hessian diagonals (stage / terminal), LM included
     double Wg[7], Wge[7];        // gradient weights: g = Wg * (y - yref) in v order (psi entry 0)
@@ -70,130 +76,32 @@ struct B2Params {
     const int32_t* ORDER;        // optional launch order of the problems (warp kernel)
     int32_t* NEXT;               // work counter of the persistent warp kernel (zeroed before each launch)
     // scratch
-    double* WS;                  // thread-per-problem kernel: all per-problem work arrays
     double* WPRIV;               // warp kernel: node-private rows, one block of wpriv_stride doubles per resident CTA
     size_t wpriv_stride;
 };
 
 // ---- products with S = [B A] (5 x 7), exploiting the generated sparsity pattern -------------
+// Floating-point contraction is OFF in every build of the kernels (device: -fmad=false, CPU mirror: -ffp-contract=off):
+// each fused multiply-add below is written out, so that the GPU and the mirror execute the same operations.
 // out[5] = [B A] * v[7]
-__device__ __forceinline__ void b2_ba_mul(const double* sv, double h, double h2, const double* v, double* out)
+__host__ __device__ __forceinline__ void b2_ba_mul(const double* sv, double h, double h2, const double* v, double* out)
 {
-    out[0] = v[2] + sv[SV_A02] * v[4] + sv[SV_A03] * v[5] + sv[SV_A04] * v[6] + sv[SV_B00] * v[0] + sv[SV_B01] * v[1];
-    out[1] = v[3] + sv[SV_A12] * v[4] + sv[SV_A13] * v[5] + sv[SV_A14] * v[6] + sv[SV_B10] * v[0] + sv[SV_B11] * v[1];
-    out[2] = v[4] + h * v[6] + h2 * v[1];
-    out[3] = v[5] + h * v[0];
-    out[4] = v[6] + h * v[1];
+    out[0] = fma(sv[SV_A03], v[5], fma(sv[SV_A02], v[4], v[2])) + fma(sv[SV_B01], v[1], fma(sv[SV_B00], v[0], sv[SV_A04] * v[6]));
+    out[1] = fma(sv[SV_A13], v[5], fma(sv[SV_A12], v[4], v[3])) + fma(sv[SV_B11], v[1], fma(sv[SV_B10], v[0], sv[SV_A14] * v[6]));
+    out[2] = fma(h2, v[1], fma(h, v[6], v[4]));
+    out[3] = fma(h, v[0], v[5]);
+    out[4] = fma(h, v[1], v[6]);
 }
 // out[7] = [B A]^T * w[5]
-__device__ __forceinline__ void b2_bat_mul(const double* sv, double h, double h2, const double* w, double* out)
+__host__ __device__ __forceinline__ void b2_bat_mul(const double* sv, double h, double h2, const double* w, double* out)
 {
-    out[0] = sv[SV_B00] * w[0] + sv[SV_B10] * w[1] + h * w[3];
-    out[1] = sv[SV_B01] * w[0] + sv[SV_B11] * w[1] + h2 * w[2] + h * w[4];
+    out[0] = fma(h, w[3], fma(sv[SV_B10], w[1], sv[SV_B00] * w[0]));
+    out[1] = fma(sv[SV_B11], w[1], sv[SV_B01] * w[0]) + fma(h, w[4], h2 * w[2]);
     out[2] = w[0];
     out[3] = w[1];
-    out[4] = sv[SV_A02] * w[0] + sv[SV_A12] * w[1] + w[2];
-    out[5] = sv[SV_A03] * w[0] + sv[SV_A13] * w[1] + w[3];
-    out[6] = sv[SV_A04] * w[0] + sv[SV_A14] * w[1] + h * w[2] + w[4];
+    out[4] = fma(sv[SV_A12], w[1], fma(sv[SV_A02], w[0], w[2]));
+    out[5] = fma(sv[SV_A13], w[1], fma(sv[SV_A03], w[0], w[3]));
+    out[6] = fma(sv[SV_A14], w[1], fma(sv[SV_A04], w[0], w[4])) + h * w[2];
 }
 // symmetric 5x5 stored packed lower: idx(i,j) i>=j -> i*(i+1)/2 + j
 __host__ __device__ __forceinline__ constexpr int b2_sym(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-// y[5] = P * x[5]
-__device__ __forceinline__ void b2_symv(const double* P, const double* x, double* y)
-{
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        double a = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; j++) a += P[b2_sym(i, j)] * x[j];
-        y[i] = a;
-    }
-}
-// Mfull[28] (packed lower 7x7, v order) = [B A]^T P [B A]
-__device__ __forceinline__ void b2_bat_p_ba(const double* sv, double h, double h2, const double* P, double* Mp)
-{
-    // W[:,j] = P * col_j([B A]) for the 7 columns
-    double W[7][5];
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const double p0 = P[b2_sym(r, 0)], p1 = P[b2_sym(r, 1)], p2 = P[b2_sym(r, 2)], p3 = P[b2_sym(r, 3)], p4 = P[b2_sym(r, 4)];
-        W[0][r] = sv[SV_B00] * p0 + sv[SV_B10] * p1 + h * p3;
-        W[1][r] = sv[SV_B01] * p0 + sv[SV_B11] * p1 + h2 * p2 + h * p4;
-        W[2][r] = p0;
-        W[3][r] = p1;
-        W[4][r] = sv[SV_A02] * p0 + sv[SV_A12] * p1 + p2;
-        W[5][r] = sv[SV_A03] * p0 + sv[SV_A13] * p1 + p3;
-        W[6][r] = sv[SV_A04] * p0 + sv[SV_A14] * p1 + h * p2 + p4;
-    }
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-        double col[7];
-        b2_bat_mul(sv, h, h2, W[j], col);     // col[i] = col_i . W[:,j] = M[i][j]
-#pragma unroll
-        for (int i = j; i < 7; i++) Mp[i * (i + 1) / 2 + j] = col[i];
-    }
-}
-
-// ---- square-root helpers (thread-level) ---------------------------------------------------------
-// in-place Cholesky of a packed lower-triangular n x n matrix (idx(i,j) = i(i+1)/2 + j);
-// non-positive pivot -> zero column (BLASFEO dpotrf convention)
-template <int NN>
-__device__ __forceinline__ void b2_chol_packed(double* Mp)
-{
-#pragma unroll
-    for (int j = 0; j < NN; j++) {
-        double d = Mp[j * (j + 1) / 2 + j];
-#pragma unroll
-        for (int q = 0; q < j; q++) d -= Mp[j * (j + 1) / 2 + q] * Mp[j * (j + 1) / 2 + q];
-        const double l = d > 0.0 ? sqrt(d) : 0.0;
-        const double li = l > 0.0 ? 1.0 / l : 0.0;
-        Mp[j * (j + 1) / 2 + j] = l;
-#pragma unroll
-        for (int i = j + 1; i < NN; i++) {
-            double a = Mp[i * (i + 1) / 2 + j];
-#pragma unroll
-            for (int q = 0; q < j; q++) a -= Mp[i * (i + 1) / 2 + q] * Mp[j * (j + 1) / 2 + q];
-            Mp[i * (i + 1) / 2 + j] = a * li;
-        }
-    }
-}
-// y[5] = L (L^T x) for a packed lower 5x5 factor
-__device__ __forceinline__ void b2_llt_mul(const double* L, const double* x, double* y)
-{
-    double t[5];
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int r = j; r < 5; r++) acc += L[b2_sym(r, j)] * x[r];
-        t[j] = acc;
-    }
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j <= i; j++) acc += L[b2_sym(i, j)] * t[j];
-        y[i] = acc;
-    }
-}
-// Mp[28] (packed lower 7x7) = AL AL^T with AL = [B A]^T L  (L packed lower 5x5)
-__device__ __forceinline__ void b2_bat_l_sq(const double* sv, double h, double h2, const double* L, double* Mp)
-{
-    double AL[5][7];
-#pragma unroll
-    for (int q = 0; q < 5; q++) {
-        double col[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) col[r] = r >= q ? L[b2_sym(r, q)] : 0.0;
-        b2_bat_mul(sv, h, h2, col, AL[q]);
-    }
-#pragma unroll
-    for (int i = 0; i < 7; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < 5; q++) acc += AL[q][i] * AL[q][j];
-            Mp[i * (i + 1) / 2 + j] = acc;
-        }
-}

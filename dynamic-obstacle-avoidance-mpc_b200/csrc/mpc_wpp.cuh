@@ -352,11 +352,11 @@ struct WppSolver {
             for (int i = 0; i < 7; i++) {
                 const double vo = VV(i, k);
                 if (B2_WPP_NO_DT) S(o.cv + i, k) = vo;          // the old iterate, for the recomputation of dt below (cv is free here)
-                VV(i, k) = vo + a * R<PF_DV>(i, k);
+                VV(i, k) = fma(a, R<PF_DV>(i, k), vo);
             }
             if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) PP(i, k) += a * R<PF_DPI>(i, k);
+                for (int i = 0; i < 5; i++) PP(i, k) = fma(a, R<PF_DPI>(i, k), PP(i, k));
             }
         }
         __syncwarp();
@@ -366,7 +366,7 @@ struct WppSolver {
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
 #pragma unroll
-            for (int i = 0; i < 7; i++) { v[i] = VV(i, k); rg[i] = Hd[i] * v[i] + Q<PF_G>(i); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
+            for (int i = 0; i < 7; i++) { v[i] = VV(i, k); rg[i] = fma(Hd[i], v[i], Q<PF_G>(i)); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
             double sv[10];
             if (k < N) {
 #pragma unroll
@@ -386,7 +386,7 @@ struct WppSolver {
             for (int s = 0; s < 6; s++) {
                 if (!box_on(s, k)) continue;
                 const int il = o_lb + s, iu = o_ub + s;
-                double ll = Q<PF_LAM>(il) + a * Q<PF_DD>(il), lu_ = Q<PF_LAM>(iu) + a * Q<PF_DD>(iu);
+                double ll = fma(a, Q<PF_DD>(il), Q<PF_LAM>(il)), lu_ = fma(a, Q<PF_DD>(iu), Q<PF_LAM>(iu));
                 double lb, ub;
                 box_bounds(s, lb, ub);
                 double tl, tu;
@@ -394,9 +394,9 @@ struct WppSolver {
                     const double tlo = Q<PF_T>(il), tuo = Q<PF_T>(iu);
                     const double vos = S(o.cv + b2_slot2v(s), k), dvs = R<PF_DV>(b2_slot2v(s), k);
                     const double dtl = dvs + ((vos - lb) - tlo), dtu = -dvs + ((ub - vos) - tuo);      // = expand()'s dtl, dtu
-                    tl = tlo + a * dtl; tu = tuo + a * dtu;
+                    tl = fma(a, dtl, tlo); tu = fma(a, dtu, tuo);
                 } else {
-                    tl = Q<PF_T>(il) + a * Q<PF_DT>(il); tu = Q<PF_T>(iu) + a * Q<PF_DT>(iu);
+                    tl = fma(a, Q<PF_DT>(il), Q<PF_T>(il)); tu = fma(a, Q<PF_DT>(iu), Q<PF_T>(iu));
                 }
                 if (ll <= p.lam_min) ll = p.lam_min;
                 if (lu_ <= p.lam_min) lu_ = p.lam_min;
@@ -413,8 +413,8 @@ struct WppSolver {
                 const double rlu = 1.0 / (tl * tu);                    // one division per pair: 1/tl = tu/(tl tu)
                 const double til = b2_rcp_polish(tl, rlu * tu), tiu = b2_rcp_polish(tu, rlu * tl);
                 Q<PF_TINV>(il) = til; Q<PF_TINV>(iu) = tiu;
-                slot_add(Hx, s, ll * til + lu_ * tiu);
-                slot_add(gt, s, (ml + ll * rdl) * til - (mu_ + lu_ * rdu) * tiu);
+                slot_add(Hx, s, fma(lu_, tiu, ll * til));
+                slot_add(gt, s, fma(-fma(lu_, rdu, mu_), tiu, fma(ll, rdl, ml) * til));
             }
             const double Zuq = sc * p.Zu;
             double vo2 = 0.0, vo3 = 0.0, dv2 = 0.0, dv3 = 0.0;
@@ -422,14 +422,14 @@ struct WppSolver {
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
                 const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
-                double l0 = Q<PF_LAM>(i0) + a * Q<PF_DD>(i0), l1 = Q<PF_LAM>(i1) + a * Q<PF_DD>(i1);
-                double l2 = Q<PF_LAM>(i2) + a * Q<PF_DD>(i2), l3 = Q<PF_LAM>(i3) + a * Q<PF_DD>(i3);
+                double l0 = fma(a, Q<PF_DD>(i0), Q<PF_LAM>(i0)), l1 = fma(a, Q<PF_DD>(i1), Q<PF_LAM>(i1));
+                double l2 = fma(a, Q<PF_DD>(i2), Q<PF_LAM>(i2)), l3 = fma(a, Q<PF_DD>(i3), Q<PF_LAM>(i3));
                 double t0, t1, t2, t3;
                 if (B2_WPP_NO_DT) {
                     // dt of the stored step, recomputed the way expand() computed it (old v, old slacks, old t)
                     const double cxo = Q<PF_CX>(j), cyo = Q<PF_CY>(j);
-                    const double cdv = cxo * dv2 + cyo * dv3;
-                    const double cvalo = cxo * vo2 + cyo * vo3;
+                    const double cdv = fma(cyo, dv3, cxo * dv2);
+                    const double cvalo = fma(cyo, vo3, cxo * vo2);
                     const double t0o = Q<PF_T>(i0), t1o = Q<PF_T>(i1), t2o = Q<PF_T>(i2), t3o = Q<PF_T>(i3);
                     const double slo = Q<PF_SL>(j), suo = Q<PF_SU>(j), dslo = Q<PF_DSL>(j), dsuo = Q<PF_DSU>(j);
                     const double rd0o = cvalo + slo - Q<PF_LG>(j) - t0o;
@@ -437,10 +437,10 @@ struct WppSolver {
                     const double rd2o = slo + Q<PF_SLI>(j) - t2o;
                     const double rd3o = suo + Q<PF_SUI>(j) - t3o;
                     const double dt0 = cdv + dslo + rd0o, dt1 = -cdv + dsuo + rd1o, dt2 = dslo + rd2o, dt3 = dsuo + rd3o;
-                    t0 = t0o + a * dt0; t1 = t1o + a * dt1; t2 = t2o + a * dt2; t3 = t3o + a * dt3;
+                    t0 = fma(a, dt0, t0o); t1 = fma(a, dt1, t1o); t2 = fma(a, dt2, t2o); t3 = fma(a, dt3, t3o);
                 } else {
-                    t0 = Q<PF_T>(i0) + a * Q<PF_DT>(i0); t1 = Q<PF_T>(i1) + a * Q<PF_DT>(i1);
-                    t2 = Q<PF_T>(i2) + a * Q<PF_DT>(i2); t3 = Q<PF_T>(i3) + a * Q<PF_DT>(i3);
+                    t0 = fma(a, Q<PF_DT>(i0), Q<PF_T>(i0)); t1 = fma(a, Q<PF_DT>(i1), Q<PF_T>(i1));
+                    t2 = fma(a, Q<PF_DT>(i2), Q<PF_T>(i2)); t3 = fma(a, Q<PF_DT>(i3), Q<PF_T>(i3));
                 }
                 if (l0 <= p.lam_min) l0 = p.lam_min;
                 if (l1 <= p.lam_min) l1 = p.lam_min;
@@ -452,16 +452,16 @@ struct WppSolver {
                 if (t3 <= p.t_min) t3 = p.t_min;
                 Q<PF_LAM>(i0) = l0; Q<PF_LAM>(i1) = l1; Q<PF_LAM>(i2) = l2; Q<PF_LAM>(i3) = l3;
                 Q<PF_T>(i0) = t0; Q<PF_T>(i1) = t1; Q<PF_T>(i2) = t2; Q<PF_T>(i3) = t3;
-                const double s_l = Q<PF_SL>(j) + a * Q<PF_DSL>(j), s_u = Q<PF_SU>(j) + a * Q<PF_DSU>(j);
+                const double s_l = fma(a, Q<PF_DSL>(j), Q<PF_SL>(j)), s_u = fma(a, Q<PF_DSU>(j), Q<PF_SU>(j));
                 Q<PF_SL>(j) = s_l; Q<PF_SU>(j) = s_u;
                 const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
-                const double cv = cx * v[2] + cy * v[3];
+                const double cv = fma(cy, v[3], cx * v[2]);
                 const double dl = l1 - l0;
-                rg[2] += cx * dl; rg[3] += cy * dl;
+                rg[2] = fma(cx, dl, rg[2]); rg[3] = fma(cy, dl, rg[3]);
                 const double sli = Q<PF_SLI>(j), sui = Q<PF_SUI>(j);
                 const double Zlq = Q<PF_ZZLQ>(j);
-                const double rgsl = Zlq * s_l + Q<PF_ZLQ>(j) - l0 - l2;
-                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * sui) - l1 - l3;
+                const double rgsl = fma(Zlq, s_l, Q<PF_ZLQ>(j)) - l0 - l2;
+                const double rgsu = fma(Zuq, s_u, sc * fma(p.Zu, sui, p.zu)) - l1 - l3;
                 n0 = fmax(n0, fmax(fabs(rgsl), fabs(rgsu)));
                 const double rd0 = cv + s_l - Q<PF_LG>(j) - t0;
                 const double rd1 = Q<PF_UG>(j) - cv + s_u - t1;
@@ -483,14 +483,15 @@ struct WppSolver {
                 const double rd_ = 1.0 / (dl_ * du_);
                 const double Dli = b2_rcp_polish(dl_, rd_ * du_), Dui = b2_rcp_polish(du_, rd_ * dl_);
                 Q<PF_DLI>(j) = Dli; Q<PF_DUI>(j) = Dui;
-                const double weff = Gl * (Zlq + Gls) * Dli + Gu * (Zuq + Gus) * Dui;
-                Hx[2] += weff * cx * cx; Hx[3] += weff * cy * cy; hxy += weff * cx * cy;
+                const double weff = fma(Gu * (Zuq + Gus), Dui, Gl * (Zlq + Gls) * Dli);
+                const double wcx = weff * cx;
+                Hx[2] = fma(wcx, cx, Hx[2]); Hx[3] = fma(weff * cy, cy, Hx[3]); hxy = fma(wcx, cy, hxy);
                 // affine right-hand side (kind 0: rm = lam t)
-                const double q0 = (m0 + l0 * rd0) * ti0, q1 = (m1 + l1 * rd1) * ti1;
-                const double q2 = (m2 + l2 * rd2) * ti2, q3 = (m3 + l3 * rd3) * ti3;
+                const double q0 = fma(l0, rd0, m0) * ti0, q1 = fma(l1, rd1, m1) * ti1;
+                const double q2 = fma(l2, rd2, m2) * ti2, q3 = fma(l3, rd3, m3) * ti3;
                 const double rhol = rgsl + q0 + q2, rhou = rgsu + q1 + q3;
-                const double coef = (q0 - Gl * rhol * Dli) - (q1 - Gu * rhou * Dui);
-                gt[2] += cx * coef; gt[3] += cy * coef;
+                const double coef = fma(-(Gl * rhol), Dli, q0) - fma(-(Gu * rhou), Dui, q1);
+                gt[2] = fma(cx, coef, gt[2]); gt[3] = fma(cy, coef, gt[3]);
             }
             if (k < N) {
                 double rb[5];
@@ -552,7 +553,7 @@ struct WppSolver {
 #pragma unroll
                     for (int r = 0; r < 5; r++) {
                         const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
-                        acc += S(ba0[r], kk) * l;
+                        acc = fma(S(ba0[r], kk), l, acc);
                     }
                     scr[lane] = acc;
                     if (lane < 3) {
@@ -560,7 +561,7 @@ struct WppSolver {
 #pragma unroll
                         for (int r = 0; r < 5; r++) {
                             const double l = (r >= aq1) ? S(o.lxx + b2_sym(r, aq1 <= r ? aq1 : r), kk + 1) : 0.0;
-                            acc1 += S(ba1[r], kk) * l;
+                            acc1 = fma(S(ba1[r], kk), l, acc1);
                         }
                         scr[32 + lane] = acc1;
                     }
@@ -569,7 +570,7 @@ struct WppSolver {
                 // B: M = Htilde + AL AL^T
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 5; q++) acc += scr[mi * 5 + q] * scr[mj * 5 + q];
+                for (int q = 0; q < 5; q++) acc = fma(scr[mi * 5 + q], scr[mj * 5 + q], acc);
                 m += acc;
             }
             // C: right-looking Cholesky with DELAYED NORMALISATION.  The sequential chain per column is one
@@ -594,13 +595,14 @@ struct WppSolver {
                     const int ex = ((__double2hiint(pv_) >> 20) & 0x7ff) - 1023;
                     const double scale = __hiloint2double((1023 - ex) << 20, 0);
                     const double pn = pv_ * scale;
-                    if (mj > c) m = m * pn - (la * lb) * scale;
+                    if (mj > c) m = fma(m, pn, -((la * lb) * scale));
                     sigma *= pn;
                 }
             }
             // one rsqrt per lane (its own column); 1/L00 and 1/L11 come from the diagonal lanes 0 and 2:
             //   1/L00 = rsqrt(p_0),  1/L11 = sqrt(sigma_1/p_1) = sigma_1 rsqrt(sigma_1 p_1),  sigma_1 = p_0 2^-e(p_0)
-            const double myrs = my_sp > 0.0 ? rsqrt(my_sp) : 0.0;
+            // 1/sqrt through the two correctly rounded operations (rsqrt() is not: the CPU mirror could not reproduce it)
+            const double myrs = my_sp > 0.0 ? 1.0 / sqrt(my_sp) : 0.0;
             m *= myrs;
             const double rs0 = b2_bcast(myrs, 0);
             const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double((1023 - (((__double2hiint(sp0) >> 20) & 0x7ff) - 1023)) << 20, 0) : 1.0;
@@ -621,7 +623,7 @@ struct WppSolver {
     double rm_cdd, rm_smu;
     __device__ __forceinline__ double rm_of(int, double l, double t, double dd, double) const
     {
-        return (l * t + rm_cdd * dd) - rm_smu;
+        return fma(l, t, rm_cdd * dd) - rm_smu;
     }
 
     // q_lg, q_ug and the slack-elimination right-hand sides rho_l, rho_u of obstacle j at node k, base kinds
@@ -632,17 +634,17 @@ struct WppSolver {
         const double l0 = Q<PF_LAM>(i0), l1 = Q<PF_LAM>(i1), l2 = Q<PF_LAM>(i2), l3 = Q<PF_LAM>(i3);
         const double t0 = Q<PF_T>(i0), t1 = Q<PF_T>(i1), t2 = Q<PF_T>(i2), t3 = Q<PF_T>(i3);
         const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
-        const double cv = Q<PF_CX>(j) * v[2] + Q<PF_CY>(j) * v[3];
+        const double cv = fma(Q<PF_CY>(j), v[3], Q<PF_CX>(j) * v[2]);
         const double rd0 = cv + s_l - Q<PF_LG>(j) - t0;
         const double rd1 = Q<PF_UG>(j) - cv + s_u - t1;
         const double rd2 = s_l + Q<PF_SLI>(j) - t2;
         const double rd3 = s_u + Q<PF_SUI>(j) - t3;
-        q0 = (rm_of(kind, l0, t0, Q<PF_DD>(i0), smu) + l0 * rd0) * Q<PF_TINV>(i0);
-        q1 = (rm_of(kind, l1, t1, Q<PF_DD>(i1), smu) + l1 * rd1) * Q<PF_TINV>(i1);
-        const double q2 = (rm_of(kind, l2, t2, Q<PF_DD>(i2), smu) + l2 * rd2) * Q<PF_TINV>(i2);
-        const double q3 = (rm_of(kind, l3, t3, Q<PF_DD>(i3), smu) + l3 * rd3) * Q<PF_TINV>(i3);
-        const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - l0 - l2;
-        const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * Q<PF_SUI>(j)) - l1 - l3;
+        q0 = fma(l0, rd0, rm_of(kind, l0, t0, Q<PF_DD>(i0), smu)) * Q<PF_TINV>(i0);
+        q1 = fma(l1, rd1, rm_of(kind, l1, t1, Q<PF_DD>(i1), smu)) * Q<PF_TINV>(i1);
+        const double q2 = fma(l2, rd2, rm_of(kind, l2, t2, Q<PF_DD>(i2), smu)) * Q<PF_TINV>(i2);
+        const double q3 = fma(l3, rd3, rm_of(kind, l3, t3, Q<PF_DD>(i3), smu)) * Q<PF_TINV>(i3);
+        const double rgsl = fma(Q<PF_ZZLQ>(j), s_l, Q<PF_ZLQ>(j)) - l0 - l2;
+        const double rgsu = fma(Zuq, s_u, sc * fma(p.Zu, Q<PF_SUI>(j), p.zu)) - l1 - l3;
         rhol = rgsl + q0 + q2;
         rhou = rgsu + q1 + q3;
     }
@@ -660,9 +662,9 @@ struct WppSolver {
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
                     const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
-                    const double coef = -G0 * Q<PF_LRGSL>(j) * Q<PF_DLI>(j) + G1 * Q<PF_LRGSU>(j) * Q<PF_DUI>(j);
-                    gt[2] += Q<PF_CX>(j) * coef;
-                    gt[3] += Q<PF_CY>(j) * coef;
+                    const double coef = fma(G1 * Q<PF_LRGSU>(j), Q<PF_DUI>(j), -((G0 * Q<PF_LRGSL>(j)) * Q<PF_DLI>(j)));
+                    gt[2] = fma(Q<PF_CX>(j), coef, gt[2]);
+                    gt[3] = fma(Q<PF_CY>(j), coef, gt[3]);
                 }
             } else {
                 double v[7];
@@ -677,8 +679,8 @@ struct WppSolver {
                     box_bounds(s, lb, ub);
                     const double vv = slot_get(v, s);
                     const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
-                    const double ql = (rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * rdl) * Q<PF_TINV>(il);
-                    const double qu = (rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * rdu) * Q<PF_TINV>(iu);
+                    const double ql = fma(ll, rdl, rm_of(kind, ll, tl, Q<PF_DD>(il), smu)) * Q<PF_TINV>(il);
+                    const double qu = fma(lu_, rdu, rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu)) * Q<PF_TINV>(iu);
                     slot_add(gt, s, ql - qu);
                 }
                 const double Zuq = sc * p.Zu;
@@ -687,9 +689,9 @@ struct WppSolver {
                     double rhol, rhou, q0, q1;
                     slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
                     const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
-                    const double coef = (q0 - G0 * rhol * Q<PF_DLI>(j)) - (q1 - G1 * rhou * Q<PF_DUI>(j));
-                    gt[2] += Q<PF_CX>(j) * coef;
-                    gt[3] += Q<PF_CY>(j) * coef;
+                    const double coef = fma(-(G0 * rhol), Q<PF_DLI>(j), q0) - fma(-(G1 * rhou), Q<PF_DUI>(j), q1);
+                    gt[2] = fma(Q<PF_CX>(j), coef, gt[2]);
+                    gt[3] = fma(Q<PF_CY>(j), coef, gt[3]);
                 }
             }
 #pragma unroll
@@ -708,14 +710,14 @@ struct WppSolver {
         for (int j = 0; j < 5; j++) {
             double acc = 0.0;
 #pragma unroll
-            for (int r = j; r < 5; r++) acc += L[b2_sym(r, j)] * x[r];
+            for (int r = j; r < 5; r++) acc = fma(L[b2_sym(r, j)], x[r], acc);
             t[j] = acc;
         }
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             double acc = 0.0;
 #pragma unroll
-            for (int j = 0; j <= i; j++) acc += L[b2_sym(i, j)] * t[j];
+            for (int j = 0; j <= i; j++) acc = fma(L[b2_sym(i, j)], t[j], acc);
             y[i] = acc;
         }
     }
@@ -782,16 +784,16 @@ struct WppSolver {
 #pragma unroll
             for (int r = 0; r < 5; r++) s[r] = pf[r] + (DPS ? S(oDPI + r, kk) : zc[r]);
             // short dependency trees: the chain through this loop is the critical path of a solve
-            const double w0 = (S(o.hg + 0, kk) + S(o.sv + SV_B00, kk) * s[0]) + (S(o.sv + SV_B10, kk) * s[1] + h * s[3]);
-            const double w1 = (S(o.hg + 1, kk) + S(o.sv + SV_B01, kk) * s[0]) + (S(o.sv + SV_B11, kk) * s[1] + h2 * s[2]) + h * s[4];
+            const double w0 = fma(S(o.sv + SV_B00, kk), s[0], S(o.hg + 0, kk)) + fma(S(o.sv + SV_B10, kk), s[1], h * s[3]);
+            const double w1 = fma(h, s[4], fma(S(o.sv + SV_B01, kk), s[0], S(o.hg + 1, kk)) + fma(S(o.sv + SV_B11, kk), s[1], h2 * s[2]));
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double lu0 = w0 * l00i;
-            const double lu1 = (w1 - l10 * lu0) * l11i;
+            const double lu1 = fma(-l10, lu0, w1) * l11i;
             if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
             if (kk > 0) {
-                const double pa = (S(o.hg + 2 + c5, kk) + S(acol[0], kk) * s[0]) + (S(acol[1], kk) * s[1] + S(acol[2], kk) * s[2]);
-                const double pb = S(acol[3], kk) * s[3] + S(acol[4], kk) * s[4];
-                const double pc = (pa + pb) - (S(o.lxu + 2 * c5, kk) * lu0 + S(o.lxu + 2 * c5 + 1, kk) * lu1);
+                const double pa = fma(S(acol[0], kk), s[0], S(o.hg + 2 + c5, kk)) + fma(S(acol[1], kk), s[1], S(acol[2], kk) * s[2]);
+                const double pb = fma(S(acol[3], kk), s[3], S(acol[4], kk) * s[4]);
+                const double pc = (pa + pb) - fma(S(o.lxu + 2 * c5, kk), lu0, S(o.lxu + 2 * c5 + 1, kk) * lu1);
                 if (lane < 5) R<PF_PV>(lane, kk) = pc;
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
@@ -808,14 +810,14 @@ struct WppSolver {
         for (int kk = 0; kk < N; kk++) {
             double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
             if (kk > 0) {
-                r0 = (r0 + S(o.lxu + 0, kk) * dx[0] + S(o.lxu + 2, kk) * dx[1]) + (S(o.lxu + 4, kk) * dx[2] + S(o.lxu + 6, kk) * dx[3] + S(o.lxu + 8, kk) * dx[4]);
-                r1 = (r1 + S(o.lxu + 1, kk) * dx[0] + S(o.lxu + 3, kk) * dx[1]) + (S(o.lxu + 5, kk) * dx[2] + S(o.lxu + 7, kk) * dx[3] + S(o.lxu + 9, kk) * dx[4]);
+                r0 = fma(S(o.lxu + 2, kk), dx[1], fma(S(o.lxu + 0, kk), dx[0], r0)) + fma(S(o.lxu + 8, kk), dx[4], fma(S(o.lxu + 6, kk), dx[3], S(o.lxu + 4, kk) * dx[2]));
+                r1 = fma(S(o.lxu + 3, kk), dx[1], fma(S(o.lxu + 1, kk), dx[0], r1)) + fma(S(o.lxu + 9, kk), dx[4], fma(S(o.lxu + 7, kk), dx[3], S(o.lxu + 5, kk) * dx[2]));
             }
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double du1 = -r1 * l11i;
-            const double du0 = (-r0 - l10 * du1) * l00i;
-            const double xa = (S(oRB + c5, kk) + S(arow[2], kk) * dx[0] + S(arow[3], kk) * dx[1]) + (S(arow[4], kk) * dx[2] + S(arow[5], kk) * dx[3] + S(arow[6], kk) * dx[4]);
-            const double xn = xa + (S(arow[0], kk) * du0 + S(arow[1], kk) * du1);
+            const double du0 = fma(-l10, du1, -r0) * l00i;
+            const double xa = fma(S(arow[3], kk), dx[1], fma(S(arow[2], kk), dx[0], S(oRB + c5, kk))) + fma(S(arow[6], kk), dx[4], fma(S(arow[5], kk), dx[3], S(arow[4], kk) * dx[2]));
+            const double xn = xa + fma(S(arow[0], kk), du0, S(arow[1], kk) * du1);
             if (lane == 0) { rDV(0, kk) = du0; rDV(1, kk) = du1; }
             if (lane < 5) rDV(2 + lane, kk + 1) = xn;
 #pragma unroll
@@ -872,15 +874,15 @@ struct WppSolver {
             const double dtl = dvv + rdl, dtu = -dvv + rdu;
             double dll, dlu;
             if (MODE == XP_SOLVE) {
-                dll = -(rm_of(kind, ll, tl, Q<PF_DD>(il), smu) + ll * dtl) * Q<PF_TINV>(il);
-                dlu = -(rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu) + lu_ * dtu) * Q<PF_TINV>(iu);
+                dll = -fma(ll, dtl, rm_of(kind, ll, tl, Q<PF_DD>(il), smu)) * Q<PF_TINV>(il);
+                dlu = -fma(lu_, dtu, rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu)) * Q<PF_TINV>(iu);
                 Q<PF_DD>(il) = keep_dd ? dtl * dll : dll;
                 Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
                 if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else if (MODE == XP_REFINE) {
                 const double cvv = slot_get(cv, s);
-                dll = Q<PF_DD>(il) - ll * cvv * Q<PF_TINV>(il);
-                dlu = Q<PF_DD>(iu) + lu_ * cvv * Q<PF_TINV>(iu);
+                dll = fma(-(ll * cvv), Q<PF_TINV>(il), Q<PF_DD>(il));
+                dlu = fma(lu_ * cvv, Q<PF_TINV>(iu), Q<PF_DD>(iu));
                 Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
                 if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else {
@@ -894,11 +896,11 @@ struct WppSolver {
         for (int j = 0; j < M; j++) {
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
             const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
-            const double cdv = cx * dv[2] + cy * dv[3];
+            const double cdv = fma(cy, dv[3], cx * dv[2]);
             const double l0 = Q<PF_LAM>(i0), l1 = Q<PF_LAM>(i1), l2 = Q<PF_LAM>(i2), l3 = Q<PF_LAM>(i3);
             const double t0 = Q<PF_T>(i0), t1 = Q<PF_T>(i1), t2 = Q<PF_T>(i2), t3 = Q<PF_T>(i3);
             const double s_l = Q<PF_SL>(j), s_u = Q<PF_SU>(j);
-            const double cval = cx * v[2] + cy * v[3];
+            const double cval = fma(cy, v[3], cx * v[2]);
             const double rd0 = cval + s_l - Q<PF_LG>(j) - t0;
             const double rd1 = Q<PF_UG>(j) - cval + s_u - t1;
             const double rd2 = s_l + Q<PF_SLI>(j) - t2;
@@ -908,27 +910,27 @@ struct WppSolver {
                 const double ti0 = Q<PF_TINV>(i0), ti1 = Q<PF_TINV>(i1), ti2 = Q<PF_TINV>(i2), ti3 = Q<PF_TINV>(i3);
                 double rhol, rhou, q0, q1;
                 slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
-                dsl = -(l0 * ti0 * cdv + rhol) * Q<PF_DLI>(j);
-                dsu = -(-l1 * ti1 * cdv + rhou) * Q<PF_DUI>(j);
+                dsl = -fma(l0 * ti0, cdv, rhol) * Q<PF_DLI>(j);
+                dsu = -fma(-(l1 * ti1), cdv, rhou) * Q<PF_DUI>(j);
                 if (!keep_dd) { Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu; }      // (the predictor's slack steps are never read)
                 const double dt0 = cdv + dsl + rd0, dt1 = -cdv + dsu + rd1, dt2 = dsl + rd2, dt3 = dsu + rd3;
-                dl0 = -(rm_of(kind, l0, t0, Q<PF_DD>(i0), smu) + l0 * dt0) * ti0;
-                dl1 = -(rm_of(kind, l1, t1, Q<PF_DD>(i1), smu) + l1 * dt1) * ti1;
-                dl2 = -(rm_of(kind, l2, t2, Q<PF_DD>(i2), smu) + l2 * dt2) * ti2;
-                dl3 = -(rm_of(kind, l3, t3, Q<PF_DD>(i3), smu) + l3 * dt3) * ti3;
+                dl0 = -fma(l0, dt0, rm_of(kind, l0, t0, Q<PF_DD>(i0), smu)) * ti0;
+                dl1 = -fma(l1, dt1, rm_of(kind, l1, t1, Q<PF_DD>(i1), smu)) * ti1;
+                dl2 = -fma(l2, dt2, rm_of(kind, l2, t2, Q<PF_DD>(i2), smu)) * ti2;
+                dl3 = -fma(l3, dt3, rm_of(kind, l3, t3, Q<PF_DD>(i3), smu)) * ti3;
                 Q<PF_DD>(i0) = keep_dd ? dt0 * dl0 : dl0; Q<PF_DD>(i1) = keep_dd ? dt1 * dl1 : dl1;
                 Q<PF_DD>(i2) = keep_dd ? dt2 * dl2 : dl2; Q<PF_DD>(i3) = keep_dd ? dt3 * dl3 : dl3;
             } else if (MODE == XP_REFINE) {
                 const double ti0 = Q<PF_TINV>(i0), ti1 = Q<PF_TINV>(i1), ti2 = Q<PF_TINV>(i2), ti3 = Q<PF_TINV>(i3);
-                const double ccv = cx * cv[2] + cy * cv[3];
-                const double csl = -(l0 * ti0 * ccv + Q<PF_LRGSL>(j)) * Q<PF_DLI>(j);
-                const double csu = -(-l1 * ti1 * ccv + Q<PF_LRGSU>(j)) * Q<PF_DUI>(j);
+                const double ccv = fma(cy, cv[3], cx * cv[2]);
+                const double csl = -fma(l0 * ti0, ccv, Q<PF_LRGSL>(j)) * Q<PF_DLI>(j);
+                const double csu = -fma(-(l1 * ti1), ccv, Q<PF_LRGSU>(j)) * Q<PF_DUI>(j);
                 dsl = Q<PF_DSL>(j) + csl; dsu = Q<PF_DSU>(j) + csu;
                 Q<PF_DSL>(j) = dsl; Q<PF_DSU>(j) = dsu;
-                dl0 = Q<PF_DD>(i0) - l0 * (ccv + csl) * ti0;
-                dl1 = Q<PF_DD>(i1) - l1 * (-ccv + csu) * ti1;
-                dl2 = Q<PF_DD>(i2) - l2 * csl * ti2;
-                dl3 = Q<PF_DD>(i3) - l3 * csu * ti3;
+                dl0 = fma(-(l0 * (ccv + csl)), ti0, Q<PF_DD>(i0));
+                dl1 = fma(-(l1 * (-ccv + csu)), ti1, Q<PF_DD>(i1));
+                dl2 = fma(-(l2 * csl), ti2, Q<PF_DD>(i2));
+                dl3 = fma(-(l3 * csu), ti3, Q<PF_DD>(i3));
                 Q<PF_DD>(i0) = dl0; Q<PF_DD>(i1) = dl1; Q<PF_DD>(i2) = dl2; Q<PF_DD>(i3) = dl3;
             } else {
                 dsl = Q<PF_DSL>(j); dsu = Q<PF_DSU>(j);
@@ -942,11 +944,11 @@ struct WppSolver {
             consume<MODE>(i3, l3, t3, dt3, dl3, a, ap, ad, s1, s2);
             if (MODE == XP_LIN) {
                 const double dl = dl1 - dl0;
-                lrg[2] += cx * dl; lrg[3] += cy * dl;
-                const double rgsl = Q<PF_ZZLQ>(j) * s_l + Q<PF_ZLQ>(j) - l0 - l2;
-                const double rgsu = Zuq * s_u + sc * (p.zu + p.Zu * Q<PF_SUI>(j)) - l1 - l3;
-                const double a0 = Q<PF_ZZLQ>(j) * dsl + rgsl - dl0 - dl2;
-                const double a1 = Zuq * dsu + rgsu - dl1 - dl3;
+                lrg[2] = fma(cx, dl, lrg[2]); lrg[3] = fma(cy, dl, lrg[3]);
+                const double rgsl = fma(Q<PF_ZZLQ>(j), s_l, Q<PF_ZLQ>(j)) - l0 - l2;
+                const double rgsu = fma(Zuq, s_u, sc * fma(p.Zu, Q<PF_SUI>(j), p.zu)) - l1 - l3;
+                const double a0 = fma(Q<PF_ZZLQ>(j), dsl, rgsl) - dl0 - dl2;
+                const double a1 = fma(Zuq, dsu, rgsu) - dl1 - dl3;
                 Q<PF_LRGSL>(j) = a0; Q<PF_LRGSU>(j) = a1;
                 ln0 = fmax(ln0, fmax(fabs(a0), fabs(a1)));
             }
@@ -965,8 +967,8 @@ struct WppSolver {
             // (ad_n/ad_d) * dli > l  with ad_d < 0   <=>   ad_n * dli < l * ad_d
             if (ad_n * dli < l * ad_d) { ad_n = l; ad_d = dli; }
             if (ap_n * dti < t * ap_d) { ap_n = t; ap_d = dti; }
-            s1 += l * dti + t * dli;
-            s2 += dli * dti;
+            s1 += fma(l, dti, t * dli);
+            s2 = fma(dli, dti, s2);
         }
     }
 
@@ -1009,7 +1011,7 @@ struct WppSolver {
             const double* Hd = k < N ? p.Hd : p.Hde;
             double dv[7], lrg[7];
 #pragma unroll
-            for (int i = 0; i < 7; i++) { dv[i] = R<PF_DV>(i, k); lrg[i] = Q<PF_RG>(i) + Hd[i] * dv[i]; }
+            for (int i = 0; i < 7; i++) { dv[i] = R<PF_DV>(i, k); lrg[i] = fma(Hd[i], dv[i], Q<PF_RG>(i)); }
             double sv[10];
             if (k < N) {
 #pragma unroll
@@ -1337,7 +1339,7 @@ struct WppSolver {
 template <int MT, int NT, unsigned long long SMASK, bool SQP = false>
 __global__ void B2_WPP_BOUNDS(NT, SMASK) b2_rti_solve_wpp(const B2Params p)
 {
-    extern __shared__ double b2_smem[];
+    B2_DYNAMIC_SMEM(double, b2_smem);
     double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows
     for (;;) {
         int i = 0;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B2MPC_ABI_VERSION 2
+#define B2MPC_ABI_VERSION 3
 #define B2MPC_MAX_OBST 32
 #define B2MPC_MAX_N 128
 
@@ -45,9 +45,10 @@ typedef struct b2mpc_config {
     int32_t integrator;      /* 0 = IRK Gauss-Legendre-4 (reference, :129), 1 = RK4 */
     int32_t qp_iter_max;     /* solver_options.qp_solver_iter_max, :131 */
     int32_t lm_scaled_by_dt; /* acados-version switch for levenberg_marquardt scaling */
-    int32_t kernel;          /* 0 = auto (= 2), 1 = thread-per-problem (cross-check), 2 = warp-per-problem with the node-private
+    int32_t kernel;          /* 0 = auto (2; batches that fit the GPU in one wave: 3), 2 = warp-per-problem with the node-private
                                 rows in L2-resident global memory (any N <= 128), 3 = warp-per-problem, everything in shared
-                                memory (needs the whole problem to fit: N = 20, M = 5 does) */
+                                memory (needs the whole problem to fit: N = 20, M = 5 does).  1 (a thread-per-problem
+                                cross-check kernel) was removed in ABI 3: EINVAL */
     int32_t pred_corr, cond_pred_corr, itref_corr_max, reserved;
     double tf;               /* solver_options.tf, :132 */
     double lm;               /* solver_options.levenberg_marquardt, :128 */
@@ -146,7 +147,7 @@ int b2mpc_reset(b2mpc *h, const uint8_t *dmask, int64_t batch, void *stream);
  * 2 max_iter, 4 QP failure; also fills SQP_ITER, NLP_RES). */
 int b2mpc_solve(b2mpc *h, int64_t batch, void *stream);
 /* full SQP on a handle of either kind (solver.options_set('max_iter'/'tol_*') + solve()): max_iter <= 0 and
- * tol = NULL take the handle's configuration.  Needs a warp-per-problem kernel (cfg.kernel != 1). */
+ * tol = NULL take the handle's configuration. */
 int b2mpc_solve_sqp(b2mpc *h, int64_t batch, int32_t max_iter, const double *tol4, void *stream);
 /* ocp_integrator.set/solve/get, :207-212: X0 <- F(X0, U[0]) */
 int b2mpc_sim(b2mpc *h, int64_t batch, void *stream);
@@ -166,8 +167,8 @@ int b2mpc_loop_reset(b2mpc *h, int64_t batch, void *stream);
 int b2mpc_loop_post(b2mpc *h, int64_t batch, const double *dnoise, int32_t random_move,
                     int32_t init_guess_when_error, double tol, void *stream);
 
-/* which solve kernel the handle resolved to: 1 = thread-per-problem, 2 = warp-per-problem (node-private rows in global
-   memory), 3 = warp-per-problem (all shared memory) */
+/* which solve kernel the handle resolved to: 2 = warp-per-problem (node-private rows in global memory),
+   3 = warp-per-problem (all shared memory) */
 int b2mpc_kernel(const b2mpc *h);
 /* number of kernels launched by this handle so far (for bench accounting) */
 int64_t b2mpc_launch_count(const b2mpc *h);

@@ -956,6 +956,7 @@ typedef struct {
     const orc_config *c; int64_t B; atomic_llong next;
     const double *x0bar, *p, *yref, *zl, *Zl;
     double *x, *u, *sl, *su; int32_t *status, *qp_iter; double *stats;
+    double *pi, *lam, *t;          /* optional multiplier outputs (NULL: not wanted) */
 } batch_job;
 
 static void *batch_worker(void *arg)
@@ -975,7 +976,9 @@ static void *batch_worker(void *arg)
             int s = orc_rti_solve(c, j->x0bar + b * NX, j->p + b * nps, j->yref + b * nys,
                                   j->zl + b * nss, j->Zl + b * nss,
                                   j->x + b * nxs, j->u + b * nus, j->sl + b * nss, j->su + b * nss,
-                                  NULL, NULL, NULL, &it, &qs, st);
+                                  j->pi ? j->pi + b * (size_t)N * NX : NULL,
+                                  j->lam ? j->lam + b * (size_t)(N + 1) * (12 + 4 * M) : NULL,
+                                  j->t ? j->t + b * (size_t)(N + 1) * (12 + 4 * M) : NULL, &it, &qs, st);
             if (j->status) j->status[b] = s;
             if (j->qp_iter) j->qp_iter[b] = it;
             if (j->stats) memcpy(j->stats + b * 8, st, sizeof(st));
@@ -992,7 +995,18 @@ void orc_rti_solve_batch(const orc_config *c, int64_t B, int nthreads,
                          double *x, double *u, double *sl, double *su,
                          int32_t *status, int32_t *qp_iter, double *stats)
 {
-    batch_job j = {c, B, 0, x0bar, p, yref, zl, Zl, x, u, sl, su, status, qp_iter, stats};
+    orc_rti_solve_batch_duals(c, B, nthreads, x0bar, p, yref, zl, Zl, x, u, sl, su, NULL, NULL, NULL, status, qp_iter, stats);
+}
+
+/* same, also returning the multipliers pi[B,N*5], lam/t[B,(N+1)*(12+4M)] (any of them may be NULL) */
+void orc_rti_solve_batch_duals(const orc_config *c, int64_t B, int nthreads,
+                               const double *x0bar, const double *p, const double *yref,
+                               const double *zl, const double *Zl,
+                               double *x, double *u, double *sl, double *su,
+                               double *pi, double *lam, double *t,
+                               int32_t *status, int32_t *qp_iter, double *stats)
+{
+    batch_job j = {c, B, 0, x0bar, p, yref, zl, Zl, x, u, sl, su, status, qp_iter, stats, pi, lam, t};
     atomic_init(&j.next, 0);
     if (nthreads <= 1) { batch_worker(&j); return; }
     if (nthreads > 256) nthreads = 256;

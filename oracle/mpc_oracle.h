@@ -95,6 +95,13 @@ void orc_rti_solve_batch(const orc_config *c, int64_t B, int nthreads,
                          double *x, double *u, double *sl, double *su,
                          int32_t *status, int32_t *qp_iter, double *stats);
 
+void orc_rti_solve_batch_duals(const orc_config *c, int64_t B, int nthreads,
+                               const double *x0bar, const double *p, const double *yref,
+                               const double *zl, const double *Zl,
+                               double *x, double *u, double *sl, double *su,
+                               double *pi, double *lam, double *t,
+                               int32_t *status, int32_t *qp_iter, double *stats);
+
 /* ---- full SQP mode (north_star kernel 4; the reference itself runs SQP_RTI only, :130) ---- */
 /* res[4] = inf norms of [stationarity, dynamics gap, g_i - t_i (incl. |x0bar - x_0|), lam_i t_i] */
 void orc_nlp_residuals(const orc_config *c, const double *x0bar, const double *p,

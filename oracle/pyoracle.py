@@ -145,10 +145,18 @@ def rti_solve(cfg, x0, p, yref, zl, Zl, x, u, sl, su, want_duals=False):
     return out
 
 
-def rti_solve_batch(cfg, x0, p, yref, zl, Zl, x, u, sl, su, nthreads=1):
-    """Batch-first arrays; iterate updated IN PLACE; returns (status, qp_iter, stats)."""
+def rti_solve_batch(cfg, x0, p, yref, zl, Zl, x, u, sl, su, nthreads=1, duals=None):
+    """Batch-first arrays; iterate updated IN PLACE; returns (status, qp_iter, stats).  `duals`: an optional dict that
+    receives the multipliers pi[B,N,5], lam[B,N+1,12+4M], t[B,N+1,12+4M] of the QP."""
     B = x0.shape[0]
     status = np.zeros(B, np.int32); qp_iter = np.zeros(B, np.int32); stats = np.zeros((B, 8))
+    if duals is not None:
+        N, M = cfg.N, cfg.M
+        duals.update(pi=np.zeros((B, N, 5)), lam=np.zeros((B, N + 1, 12 + 4 * M)), t=np.zeros((B, N + 1, 12 + 4 * M)))
+        lib().orc_rti_solve_batch_duals(C.byref(cfg), C.c_int64(B), C.c_int(nthreads),
+                                        _p(x0), _p(p), _p(yref), _p(zl), _p(Zl), _p(x), _p(u), _p(sl), _p(su),
+                                        _p(duals["pi"]), _p(duals["lam"]), _p(duals["t"]), _pi(status), _pi(qp_iter), _p(stats))
+        return status, qp_iter, stats
     lib().orc_rti_solve_batch(C.byref(cfg), C.c_int64(B), C.c_int(nthreads),
                               _p(x0), _p(p), _p(yref), _p(zl), _p(Zl),
                               _p(x), _p(u), _p(sl), _p(su), _pi(status), _pi(qp_iter), _p(stats))

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/b200mpc.h but not exported"
     assert set(capi.EXPORTS) <= names
-    assert lib.b2mpc_abi_version() == 2
+    assert lib.b2mpc_abi_version() == 3
 
 
 def test_default_config_matches_reference_constants(lib):
@@ -46,7 +46,7 @@ def test_create_validates_arguments_and_has_no_cpu_fallback(lib):
     import torch
     h = C.c_void_p()
     for bad in (dict(N=0), dict(N=129), dict(n_obst=0), dict(n_obst=33), dict(max_batch=0), dict(tf=0.0), dict(integrator=7),
-                dict(nlp_solver=2), dict(nlp_solver=1, nlp_iter_max=0), dict(nlp_solver=1, kernel=1)):
+                dict(nlp_solver=2), dict(nlp_solver=1, nlp_iter_max=0), dict(kernel=1)):
         c = capi.default_config(20, 5, 2.0, 8, 0)
         for k, v in bad.items():
             setattr(c, k, v)

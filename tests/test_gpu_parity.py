@@ -1,6 +1,18 @@
-"""GPU parity tests (run on the B200 box): the CUDA path, called through the C-ABI, against the CPU
-oracle on identical seeded inputs.  Bar (BASELINE.json north_star): identical interior-point
-iteration counts and status, u and predicted states within 1e-6 relative."""
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C-ABI, against
+
+  (1) the CPU MIRROR of the kernels (oracle/simt/: the kernel source executed by a SIMT emulator; explicit fma() on both
+      sides, contraction off): every output of EVERY problem must be BIT-IDENTICAL -- iterates, multipliers, slacks and
+      interior-point iteration counts, converged or not;
+  (2) the INDEPENDENT oracle (oracle/mpc_oracle.c: different code, plain Cholesky, sequential sums): north_star's bar --
+      u and predicted states within 1e-6 relative, identical iteration counts and status -- with the tolerance written
+      here.  Two implementations with different rounding cannot agree bit for bit; where they may differ is spelled out
+      and bounded: see _check_independent().
+
+There is no waiver for QPs that run into qp_solver_iter_max: against the mirror they are bit-identical, against the
+independent oracle they are compared at truncated iteration limits (5/10/20/30: both sides stop at the same iteration, ALL
+problems within 1e-6) and at the full limit with a quantile bar."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,19 +20,19 @@ from b200mpc import world
 
 pytestmark = pytest.mark.gpu
 
-REL_TOL = 1e-6          # north_star tolerance for u0 / predicted states (converged QPs)
-REL_TOL_MAXITER = 1.0   # QPs stopped by qp_solver_iter_max are NOT at a KKT point: the returned iterate
-                        # depends on the path taken, rounding differences are amplified (median 1e-10, rare
-                        # outliers up to 0.2 of the control range).  Sanity bound only (finite, inside the
-                        # bounds) -- the parity bar applies to converged QPs.
-MIN_ITER_MATCH = 0.99   # identical interior-point iteration counts on >= 99 % of the problems (observed
-                        # 99.6-99.9 %).  The rest: (a) the HPIPM exit test compares res_g with 1e-6, which after
-                        # a full Newton step IS the rounding residual of the linear solve (slack-bound rows carry
-                        # lam/t ~ 1e18) -> +-1 iteration; (b) slowly converging QPs (30-50 iterations of tiny
-                        # steps) are chaotic in the rounding -> larger differences, < 0.5 % of the problems.
-MIN_ITER_MATCH_LONG = 0.98   # horizons beyond the reference's N=20 with more obstacles: longer recursions, more slowly
-                        # converging QPs; observed 99.1-99.3 % on 1024 problems for ALL kernels (scripts/dump_parity.py)
-MAX_OUTLIERS = 0.01     # fraction of problems allowed to differ by more than one iteration
+REL_TOL = 1e-6          # north_star tolerance for u0 / predicted states
+# Independent oracle, iteration counts.  The HPIPM exit test compares res_g with 1e-6, which after a full Newton step IS the
+# rounding residual of the linear solve (slack-bound rows carry lam/t ~ 1e18): two correct implementations with different
+# rounding disagree by one iteration on a few problems per thousand, and QPs that crawl for 30-50 iterations with step
+# lengths of 1e-4 amplify rounding differences.  Measured on the headline workload (4096 cold scenarios): 10 of 4096 differ.
+MIN_ITER_MATCH = 0.995
+MIN_ITER_MATCH_LONG = 0.98   # horizons beyond the reference's N=20 with more obstacles (observed 99.1-99.3 %)
+MAX_OUTLIERS = 0.005    # fraction of problems allowed to differ by more than one iteration
+# Independent oracle, QPs stopped by the full iteration limit (not at a KKT point; 50 iterations of amplification):
+CAPPED_Q = 0.95         # >= 95 % of them within REL_TOL (measured 95.8 %: 52 of 1239 outside), ...
+CAPPED_MEDIAN = 1e-9    # ... the median far below it (measured 1e-13)
+FIELDS = ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")
+NTHREADS = min(os.cpu_count() or 1, 32)
 
 
 @pytest.fixture(scope="module")
@@ -31,22 +43,48 @@ def torch_cuda():
     return torch
 
 
-def _solve_both(torch, oracle, dims, sc, B, **cfg_over):
+@pytest.fixture(scope="module")
+def mirror():
+    from oracle import pymirror
+    pymirror.build()
+    return pymirror
+
+
+def _solve_gpu(torch, dims, sc, B, **cfg_over):
     from b200mpc import BatchedMpcSolver
     solver = BatchedMpcSolver(dims.N, dims.M, dims.tf, max_batch=B, device=0, **cfg_over)
-    for name in ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su"):
+    for name in FIELDS:
         solver.set(name, torch.from_numpy(sc[name]).cuda())
     solver.solve(B)
     out = {k: solver.get(k, B).cpu().numpy() for k in ("x", "u", "sl", "su", "pi", "lam", "t", "stats")}
-    out["qp_iter"] = solver.get_int("qp_iter", B).cpu().numpy()
-    out["status"] = solver.get_int("status", B).cpu().numpy()
+    for k in ("qp_iter", "status", "qp_status"):
+        out[k] = solver.get_int(k, B).cpu().numpy()
+    out["kernel"] = solver.kernel_id
     solver.close()
+    return out
+
+
+def _solve_oracle(oracle, dims, sc, **cfg_over):
     cfg = oracle.default_config(dims.N, dims.M, dims.tf, **{k: v for k, v in cfg_over.items() if k != "kernel"})
     ref = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    duals = {}
     st, it, stats = oracle.rti_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"],
-                                           ref["x"], ref["u"], ref["sl"], ref["su"], nthreads=8)
-    ref.update(status=st, qp_iter=it, stats=stats)
-    return out, ref
+                                           ref["x"], ref["u"], ref["sl"], ref["su"], nthreads=NTHREADS, duals=duals)
+    ref.update(status=st, qp_iter=it, stats=stats, **duals)
+    return ref
+
+
+def _solve_mirror(mirror, dims, sc, layout, **cfg_over):
+    cfg = mirror.default_config(dims.N, dims.M, dims.tf, **{k: v for k, v in cfg_over.items() if k != "kernel"})
+    m = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    out = mirror.solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], m["x"], m["u"], m["sl"], m["su"],
+                             layout=layout, nthreads=NTHREADS)
+    m.update(out)
+    return m
+
+
+def _solve_both(torch, oracle, dims, sc, B, **cfg_over):
+    return _solve_gpu(torch, dims, sc, B, **cfg_over), _solve_oracle(oracle, dims, sc, **cfg_over)
 
 
 def _rel(a, b):
@@ -59,34 +97,88 @@ def _rel_rows(a, b):
     return np.abs(a - b).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(b).reshape(B, -1).max(1))
 
 
-def _check_parity(out, ref, qp_iter_max=50, min_iter_match=MIN_ITER_MATCH):
-    assert (out["status"] == ref["status"]).all()
+def _check_bit_identical(out, mir):
+    """GPU against the CPU mirror: every problem, every output, bit for bit"""
+    for k in ("qp_iter", "status", "qp_status", "x", "u", "sl", "su", "pi", "lam", "t"):
+        assert np.array_equal(out[k], mir[k]), (k, np.nonzero(np.any((out[k] != mir[k]).reshape(out[k].shape[0], -1), axis=1))[0][:8])
+    assert np.array_equal(out["stats"][:, :7], mir["stats"][:, :7])
+
+
+def _check_independent(out, ref, qp_iter_max=50, min_iter_match=MIN_ITER_MATCH):
+    """GPU against the independent oracle at the full iteration limit.  Returns the mask of converged problems."""
+    B = out["qp_iter"].size
+    # a solve whose linear algebra breaks down (res_g explodes, step length -> alpha_min) can end as QP failure (4) on one
+    # side and as max-iter on the other: at most one problem per thousand
+    assert (out["status"] != ref["status"]).sum() <= max(1, B // 1000)
     same = out["qp_iter"] == ref["qp_iter"]
-    B = same.size
     assert (~same).sum() <= max(1, int((1 - min_iter_match) * B)), (same.mean(), np.nonzero(~same))
     assert (np.abs(out["qp_iter"] - ref["qp_iter"]) > 1).sum() <= max(1, int(MAX_OUTLIERS * B))
     # converged = both stopped before the iteration limit with the KKT residuals below the HPIPM tolerances
-    # (a solve can also stop on the minimum step length -> status 4, iterate untouched)
     rs = ref["stats"]
-    conv = (ref["qp_iter"] < qp_iter_max) & (out["qp_iter"] < qp_iter_max) & (ref["status"] == 0) & \
+    conv = (ref["qp_iter"] < qp_iter_max) & (out["qp_iter"] < qp_iter_max) & (ref["status"] == 0) & (out["status"] == 0) & \
            (rs[:, 0] <= 1e-6) & (rs[:, 1] <= 1e-8) & (rs[:, 2] <= 1e-8) & (rs[:, 3] <= 1e-8)
+    capped = (ref["qp_iter"] == qp_iter_max) & (out["qp_iter"] == qp_iter_max)
     for k in ("u", "x"):
         e = _rel_rows(out[k], ref[k])
         assert e[conv].max() < REL_TOL, (k, e[conv].max())
-        if (~conv).any():
-            assert e[~conv].max() < REL_TOL_MAXITER, (k, e[~conv].max())
+        if capped.sum() >= 40:
+            assert np.quantile(e[capped], CAPPED_Q) < REL_TOL, (k, np.quantile(e[capped], CAPPED_Q))
+            assert np.median(e[capped]) < CAPPED_MEDIAN
     return conv
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["thread-per-problem", "warp-per-problem", "warp-per-problem-all-shared"])
-@pytest.mark.parametrize("N,M,tf,B", [(20, 5, 2.0, 512), (5, 5, 0.5, 300), (10, 3, 1.0, 257), (30, 8, 3.0, 400)])
-def test_rti_solve_matches_oracle(torch_cuda, oracle, N, M, tf, B, kernel):
+def test_headline_workload_every_problem(torch_cuda, oracle, mirror):
+    """The bench configuration itself (bench.py: 4096 random scenarios, seed 0, cold set_initial_guess iterate, N=20, Tf=2 s,
+    5 obstacles): bit-identical to the mirror on all 4096 problems, north_star's bar against the independent oracle."""
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 4096
+    sc = world.random_scenarios(B, dims, seed=0)
+    out = _solve_gpu(torch_cuda, dims, sc, B)
+    assert out["kernel"] == 2                                   # the persistent throughput kernel (what bench.py times)
+    _check_bit_identical(out, _solve_mirror(mirror, dims, sc, 2))
+    ref = _solve_oracle(oracle, dims, sc)
+    conv = _check_independent(out, ref)
+    assert 0.6 < conv.mean() < 0.8
+    assert out["qp_iter"].sum() == 127908, out["qp_iter"].sum()     # the number bench.py prints as mean_qp_iter * 4096
+    assert abs(int(ref["qp_iter"].sum()) - 127908) <= 64
+    # multipliers and active sets of the converged problems
+    for k in ("lam", "t", "pi"):
+        assert _rel_rows(out[k], ref[k])[conv].max() < 1e-5, k
+    assert np.array_equal(out["lam"][conv] > 1e-4, ref["lam"][conv] > 1e-4)
+
+
+@pytest.mark.parametrize("qp_iter_max", [5, 10, 20, 30])
+def test_truncated_iteration_parity_all_problems(torch_cuda, oracle, mirror, qp_iter_max):
+    """Both implementations stopped at the SAME interior-point iteration: every problem of the headline workload --
+    also the 30 % that never converge within the reference's limit -- agrees within 1e-6 (u, x) and 1e-5 of the
+    largest multiplier; rounding differences need tens of iterations to grow."""
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 2048
+    sc = world.random_scenarios(B, dims, seed=0)
+    out = _solve_gpu(torch_cuda, dims, sc, B, qp_iter_max=qp_iter_max)
+    ref = _solve_oracle(oracle, dims, sc, qp_iter_max=qp_iter_max)
+    assert (out["status"] == ref["status"]).all()
+    assert np.mean(out["qp_iter"] == ref["qp_iter"]) >= 0.998 and np.abs(out["qp_iter"] - ref["qp_iter"]).max() <= 1
+    assert _rel_rows(out["u"], ref["u"]).max() < REL_TOL
+    assert _rel_rows(out["x"], ref["x"]).max() < REL_TOL
+    assert _rel_rows(out["sl"][:, :-1], ref["sl"][:, :-1]).max() < 1e-5
+    if qp_iter_max <= 10:
+        assert (out["qp_iter"] == qp_iter_max).all()             # nothing converges that early: all problems are truncated
+        for k in ("lam", "t", "pi"):
+            assert _rel_rows(out[k], ref[k]).max() < 1e-5, k
+    if qp_iter_max == 20:
+        _check_bit_identical(out, _solve_mirror(mirror, dims, sc, 2, qp_iter_max=qp_iter_max))
+
+
+@pytest.mark.parametrize("kernel,layout", [(2, 2), (3, 3)], ids=["warp-per-problem", "warp-per-problem-all-shared"])
+@pytest.mark.parametrize("N,M,tf,B", [(20, 5, 2.0, 512), (5, 5, 0.5, 300), (10, 3, 1.0, 257), (10, 5, 1.0, 256), (30, 8, 3.0, 400)])
+def test_rti_solve_matches_mirror_and_oracle(torch_cuda, oracle, mirror, N, M, tf, B, kernel, layout):
     dims = world.MpcDims(N, M, tf)
     sc = world.random_scenarios(B, dims, seed=5, moving_start=True)
     out, ref = _solve_both(torch_cuda, oracle, dims, sc, B, kernel=kernel)
-    conv = _check_parity(out, ref, min_iter_match=MIN_ITER_MATCH if N <= 20 else MIN_ITER_MATCH_LONG)
+    _check_bit_identical(out, _solve_mirror(mirror, dims, sc, layout))
+    conv = _check_independent(out, ref, min_iter_match=MIN_ITER_MATCH if N <= 20 else MIN_ITER_MATCH_LONG)
     assert conv.mean() > 0.3          # the comparison below must not be vacuous
-    # slack iterates are weakly determined (zero cost on the upper side / at the terminal node)
     # lower slacks of the penalised nodes are part of the solution; the upper slacks (zero cost, uh = 1e5 never
     # active) and the terminal-node slacks (alpha_N = 0) are free directions of the QP and are not compared
     assert _rel_rows(out["sl"][:, :-1], ref["sl"][:, :-1])[conv].max() < 1e-5
@@ -114,15 +206,16 @@ def test_active_set_matches_oracle(torch_cuda, oracle):
         assert _rel(out["pi"][b], r["pi"]) < 1e-5
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
-def test_rk4_variant_matches_oracle(torch_cuda, oracle, kernel):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_rk4_variant_matches_oracle(torch_cuda, oracle, mirror, kernel):
     dims = world.MpcDims(20, 5, 2.0)
     sc = world.random_scenarios(64, dims, seed=2, moving_start=True)
     out, ref = _solve_both(torch_cuda, oracle, dims, sc, 64, integrator=1, kernel=kernel)
-    _check_parity(out, ref)
+    _check_bit_identical(out, _solve_mirror(mirror, dims, sc, kernel, integrator=1))
+    _check_independent(out, ref)
 
 
-def test_closed_loop_tracks_oracle(torch_cuda, oracle):
+def test_closed_loop_tracks_oracle(torch_cuda, oracle, mirror):
     """25 closed-loop control steps (solve -> plant step -> obstacle step -> shift) on 64 scenarios;
     per-step parity stays within tolerance while both loops see identical inputs."""
     torch = torch_cuda
@@ -143,14 +236,20 @@ def test_closed_loop_tracks_oracle(torch_cuda, oracle):
         solver.set("p", torch.from_numpy(p).cuda())
         solver.prepare_slack(B)
         solver.solve(B)
+        # the mirror sees what the GPU sees (the iterate both start from is the oracle's of the previous step): bit-identical
+        mir = {k: ref[k].copy() for k in ("x", "u", "sl", "su")}
+        zl_gpu, Zl_gpu = solver.get("zl", B).cpu().numpy(), solver.get("Zl", B).cpu().numpy()
+        mo = mirror.solve_batch(mirror.default_config(20, 5, 2.0), x0, p, sc["yref"], zl_gpu, Zl_gpu, mir["x"], mir["u"], mir["sl"], mir["su"],
+                                layout=3, nthreads=NTHREADS)          # 64 problems fit the GPU in one wave: all-shared kernel
         st_o, it_o, _ = oracle.rti_solve_batch(cfg, x0, p, sc["yref"], zl, Zl, ref["x"], ref["u"], ref["sl"], ref["su"], nthreads=8)
         u_gpu = solver.get("u", B).cpu().numpy()
         it_gpu = solver.get_int("qp_iter", B).cpu().numpy()
-        assert _rel(solver.get("zl", B).cpu().numpy(), zl) < 1e-14
+        assert np.array_equal(u_gpu, mir["u"]) and np.array_equal(it_gpu, mo["qp_iter"]), step
+        assert np.array_equal(solver.get("x", B).cpu().numpy(), mir["x"]), step
+        assert _rel(zl_gpu, zl) < 1e-14
         conv = (it_o < 50) & (it_gpu < 50)
         e = _rel_rows(u_gpu, ref["u"])
         assert e[conv].max() < REL_TOL, step
-        assert e.max() < REL_TOL_MAXITER, step
         assert np.mean(it_gpu == it_o) >= 0.9 and np.mean(np.abs(it_gpu - it_o) > 1) <= 0.05, (step, it_gpu, it_o)
         # plant + shift on both sides; keep the two loops on identical states (oracle's) so that
         # chaotic divergence of the closed loop does not mask per-step parity
@@ -205,21 +304,25 @@ def test_reset_mask_and_errors(torch_cuda):
     solver.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
-def test_long_horizon_many_obstacles(torch_cuda, oracle, kernel):
-    """BASELINE config 4 shape (N=100, Tf=5 s, 20 obstacles): the warp kernel walks the 101 nodes in four
-    passes of 32 lanes with the node-private rows in global memory (selected automatically); the
-    thread-per-problem kernel stays available as a cross-check."""
+def test_long_horizon_many_obstacles(torch_cuda, oracle, mirror):
+    """BASELINE config 4 (N=100, Tf=5 s, 20 obstacles) at B = 1024: the warp kernel walks the 101 nodes in four passes of 32
+    lanes with the node-private rows (and v, pi, dv, dpi, ...) in global memory.  Independent oracle on all 1024 problems,
+    the CPU mirror (about a second per problem and core) bit for bit on the first 96 -- per-problem results do not depend on
+    the batch they are solved in."""
     from b200mpc import BatchedMpcSolver
     dims = world.MpcDims(100, 20, 5.0)
-    B = 24
+    B, Bm = 1024, 96
     sc = world.random_scenarios(B, dims, seed=8)
-    out, ref = _solve_both(torch_cuda, oracle, dims, sc, B, kernel=kernel)
-    _check_parity(out, ref, min_iter_match=0.9)
-    if kernel == 0:
-        s = BatchedMpcSolver(100, 20, 5.0, max_batch=B)
-        assert s.kernel_name == "warp-per-problem"
-        s.close()
+    out, ref = _solve_both(torch_cuda, oracle, dims, sc, B)
+    assert out["kernel"] == 2
+    conv = _check_independent(out, ref, min_iter_match=0.97)
+    assert conv.mean() > 0.2
+    sub = {k: np.ascontiguousarray(v[:Bm]) for k, v in sc.items()}
+    mir = _solve_mirror(mirror, dims, sub, 2)
+    _check_bit_identical({k: (v[:Bm] if isinstance(v, np.ndarray) else v) for k, v in out.items()}, mir)
+    s = BatchedMpcSolver(100, 20, 5.0, max_batch=8)
+    assert s.kernel_name == "warp-per-problem"
+    s.close()
 
 
 def test_auto_mode_picks_the_layout_by_batch_size(torch_cuda):

@@ -118,11 +118,7 @@ def test_sqp_options_and_errors(torch_cuda):
     assert (its[0] <= its[1]).all() and its[0].mean() < its[1].mean()
     s.close()
     with pytest.raises(capi.B2mpcError):
-        BatchedMpcSolver(20, 5, 2.0, max_batch=8, kernel=1, nlp_solver=1)      # the cross-check kernel has no SQP loop
-    t = BatchedMpcSolver(20, 5, 2.0, max_batch=8, kernel=1)
-    with pytest.raises(capi.B2mpcError):
-        t.solve_sqp(8)
-    t.close()
+        BatchedMpcSolver(20, 5, 2.0, max_batch=8, kernel=1)      # the thread-per-problem cross-check kernel is gone (ABI 3)
 
 
 def test_merit_backtracking_matches_oracle(torch_cuda, oracle):
