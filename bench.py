@@ -49,12 +49,21 @@ def parse_args():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 2 warp-per-problem (node-private rows in global memory), 3 warp-per-problem all-shared")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (0 = auto)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE configs 1/3/4/5 (extra keys of the JSON line)")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"batched SQP-RTI, {a.batch_per_gpu} random start/obstacle scenarios per GPU, N={a.N}, "
             f"Tf={a.tf:g} s, {a.n_obst} moving obstacles, cold start (set_initial_guess iterate)")
+
+
+def config_dict(a, n_gpus):
+    """the SAME dictionary in both arms (b200 / reference) for the same command line: what is measured, not how"""
+    return {"workload": workload_name(a), "global_batch": int(a.batch_per_gpu * n_gpus),
+            "l2": "GPU arm: flushed between steps (256 MiB memset), both outside the per-step event pairs; CPU arm: not applicable",
+            "kernel": {0: "auto", 2: "warp-per-problem", 3: "warp-per-problem (all shared)"}.get(a.kernel, str(a.kernel)),
+            "parallelism": f"env-sharded x{n_gpus}, no data-path collective"}
 
 
 class ClockSampler:
@@ -143,7 +152,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample_per_step": sample},
+        "config": config_dict(a, a.gpus),
+        "sample_per_step": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} problems of the same workload per step, pthreads over problems, "
                                    "oracle/mpc_oracle.c (CPU restatement of the acados algorithm -- not acados)"},
@@ -223,6 +233,7 @@ def main():
     total_ms = float(np.sum(step_ms))
     qp_iter = solver.get_int("qp_iter", B).cpu().numpy()
     status = solver.get_int("status", B).cpu().numpy()
+    u_device_path = solver.get("u", B).cpu().numpy()          # result of the device-resident path (compared with the host path below)
     # restore()'s 4 layout kernels per step are not the solve; count the solve launches only
     gpu_launches = (l1 - l0) - 4 * a.steps
 
@@ -247,8 +258,8 @@ def main():
     e2e_s = float(np.sum([step_host() for _ in range(e2e_steps)]))
     h2d = sum(host[k].nbytes for k in names_in) + sum(host_it[k].nbytes for k in names_it)
     d2h = sum(host_it[k].nbytes for k in names_it) + 2 * 4 * B
-    # device result of the host path equals the device path
-    assert np.array_equal(host_it["u"], solver.get("u", B).cpu().numpy())
+    # the host path (fresh H2D copies of every input) reproduces the device-resident path bit for bit
+    assert np.array_equal(host_it["u"], u_device_path)
 
     # ---------------- steady state: the same solve on WARM iterates ----------------
     # 50 closed-loop control steps on device (obstacle prediction, slack weights, solve, plant/obstacle step, shift:
@@ -257,9 +268,7 @@ def main():
     solver.set("x0", dev_t["x0"]); solver.set("obst", torch.from_numpy(sc["obst"]).to(dev)); solver.set("goal", torch.from_numpy(sc["goal"]).to(dev))
     solver.set("yref", dev_t["yref"])
     restore(); solver.loop_reset(B)
-    for _ in range(K_WARM):
-        solver.obst_predict(B); solver.prepare_slack(B); solver.solve(B)
-        solver.loop_post(B, None, False, True, world.TOL)
+    solver.closed_loop(B, K_WARM, random_move=False, init_guess_when_error=True, tol=-1.0)   # tol < 0: nobody "reaches the goal"
     solver.obst_predict(B); solver.prepare_slack(B)
     warm = {k: solver.get(k, B).clone() for k in names_it}
 
@@ -280,6 +289,22 @@ def main():
     torch.cuda.synchronize(dev)
     warm_ms = float(np.sum([e0.elapsed_time(e1) for e0, e1 in wevs]))
     warm_it = float(solver.get_int("qp_iter", B).sum().item())
+    kernel_name = solver.kernel_name
+
+    # ---------------- on-device closed loop (b2mpc_closed_loop): env-steps/s against the warm solve rate ----------------
+    def closed_loop_rate(s, nb, steps, sc_):
+        s.set("x0", torch.from_numpy(sc_["x0"]).to(dev)); s.set("obst", torch.from_numpy(sc_["obst"]).to(dev))
+        s.set("goal", torch.from_numpy(sc_["goal"]).to(dev)); s.set("yref", torch.from_numpy(sc_["yref"]).to(dev))
+        s.loop_reset(nb); s.reset(nb)
+        s.closed_loop(nb, 10, random_move=True, seed=1, tol=-1.0)           # warm-up: leaves warm-started problems behind
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        s.closed_loop(nb, steps, random_move=True, seed=1, tol=-1.0)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps, float(s.get_int("qp_iter", nb).float().mean().item())
+
+    cl_ms, cl_it = closed_loop_rate(solver, B, 40, sc)
 
     # ---------------- p50 latency of ONE problem (the reference's one-at-a-time use) ----------------
     lat1 = None
@@ -297,11 +322,80 @@ def main():
             if i >= 10:
                 lat.append(e0.elapsed_time(e1))
         lat1 = float(np.median(lat))
+        # BASELINE config 1: one closed-loop episode (B = 1), ms per control step through the fused entry
+        sc1 = {k: np.ascontiguousarray(v[:1]) for k, v in sc.items()}
+        cfg1_ms, cfg1_it = closed_loop_rate(s1, 1, 100, sc1)
         s1.close()
+
+    # ---------------- BASELINE configs 3 / 4 / 5 (extra keys; the headline above stays configs[1]) ----------------
+    extra = {}
+    if not a.no_extra_configs:
+        solver.close()
+        del dev_t, warm
+
+        def timed_cold_solves(N_, M_, tf_, nb, reps, seed):
+            d_ = world.MpcDims(N_, M_, tf_)
+            sc_ = sharding.shard_dict(world.random_scenarios(nb * world_size, d_, seed=seed), rank, world_size)
+            s_ = BatchedMpcSolver(N_, M_, tf_, max_batch=nb, device=local_rank)
+            t_ = {k: torch.from_numpy(sc_[k]).to(dev) for k in names_in + names_it}
+            for k in names_in:
+                s_.set(k, t_[k])
+            ms_ = []
+            for i in range(reps + 1):
+                for k in names_it:
+                    s_.set(k, t_[k])
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream); s_.solve(nb); e1.record(stream); torch.cuda.synchronize(dev)
+                if i > 0:
+                    ms_.append(e0.elapsed_time(e1))
+            it_ = float(s_.get_int("qp_iter", nb).float().sum().item())
+            name_ = s_.kernel_name
+            s_.close()
+            return float(np.mean(ms_)), it_, name_
+
+        def cfg_entry(N_, M_, nb, ms_, it_sum, what):
+            sm_, mx_ = sharding.reduce_stats({"B": nb, "it": it_sum}, {"ms": ms_}, device=dev)
+            mit = sm_["it"] / sm_["B"]
+            fl_ = flops.flops_per_solve(N_, M_, mit) * nb
+            tf_ach = fl_ / (ms_ * 1e-3) / 1e12
+            return {"what": what, "value": sm_["B"] / (mx_["ms"] * 1e-3), "unit": UNIT, "ms_per_step": mx_["ms"], "global_batch": int(sm_["B"]),
+                    "mean_qp_iter": mit,
+                    "roofline": {"bound": "fp64", "achieved": tf_ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_ach / peak_tf if peak_tf else None}}
+
+        nb3 = 262144 // world_size
+        ms3, it3, _ = timed_cold_solves(a.N, a.n_obst, a.tf, nb3, 2, a.seed)
+        extra["config3"] = cfg_entry(a.N, a.n_obst, nb3, ms3, it3, f"262144 scenarios env-sharded over {world_size} GPU(s): {nb3} per GPU, N={a.N}, {a.n_obst} obstacles, cold start")
+        ms4, it4, _ = timed_cold_solves(100, 20, 5.0, 4096, 2, a.seed)
+        extra["config4"] = cfg_entry(100, 20, 4096, ms4, it4, "long horizon N=100, Tf=5 s, 20 dynamic obstacles, 4096 scenarios per GPU, cold start")
+        # config 5: RL loop (src/train.py API) over 65536 parallel environments in total, 5 MPC control steps per env step
+        from b200mpc.rl_env import BatchedMpcEnv
+        nb5 = 65536 // world_size
+        env = BatchedMpcEnv(nb5, mpc_steps=5, max_env_steps=1000, seed=3 + rank, device=local_rank)
+        env.reset()
+        env.step(env.goal)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n_env_steps = 3
+        for _ in range(n_env_steps):
+            env.step(env.goal)
+        torch.cuda.synchronize(dev)
+        dt5 = (time.perf_counter() - t0) / n_env_steps
+        it5 = float(env.ocp.solver.get_int("qp_iter", nb5).float().sum().item())
+        env.close()
+        sm5, mx5 = sharding.reduce_stats({"B": nb5, "it": it5}, {"s": dt5}, device=dev)
+        mit5 = sm5["it"] / sm5["B"]
+        fl5 = flops.flops_per_solve(20, 5, mit5) * nb5 * 5
+        extra["config5"] = {"what": f"RL loop (train.py API: reset/step, action = sub-goal) over {int(sm5['B'])} parallel environments, "
+                                    "5 MPC control steps per env step, wall clock incl. observation D2H and Python",
+                            "value": sm5["B"] * 5 / mx5["s"], "unit": UNIT, "env_steps_per_s": sm5["B"] / mx5["s"], "global_batch": int(sm5["B"]),
+                            "mean_qp_iter": mit5,
+                            "roofline": {"bound": "fp64", "achieved": fl5 / dt5 / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                         "frac": fl5 / dt5 / 1e12 / peak_tf if peak_tf else None}}
 
     # ---------------- reduce over ranks (max time; sum of work) ----------------
     sums, maxs = sharding.reduce_stats({"B": B, "qp_iter": float(qp_iter.sum()), "fail": float((status != 0).sum()), "warm_it": warm_it},
-                                       {"total_ms": total_ms, "e2e_s": e2e_s, "warm_ms": warm_ms}, device=dev)
+                                       {"total_ms": total_ms, "e2e_s": e2e_s, "warm_ms": warm_ms, "cl_ms": cl_ms}, device=dev)
     total_ms_max, e2e_s_max = maxs["total_ms"], maxs["e2e_s"]
     tot_B, tot_it, tot_fail = sums["B"], sums["qp_iter"], sums["fail"]
 
@@ -323,7 +417,7 @@ def main():
         traffic = None                       # dram__bytes_read+write of the solve kernel, one ncu --set full capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if tr.get("kernel") == solver.kernel_name and tr.get("batch") == B and (a.N, a.n_obst) == (tr.get("N"), tr.get("M")):
+            if tr.get("kernel") == kernel_name and tr.get("batch") == B and (a.N, a.n_obst) == (tr.get("N"), tr.get("M")):
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -331,9 +425,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "global_batch": int(tot_B), "l2": "flushed between steps (256 MiB memset)",
-                       "kernel": solver.kernel_name,
-                       "parallelism": f"env-sharded x{world_size}, no data-path collective"},
+            "config": config_dict(a, world_size),
+            "kernel_resolved": kernel_name,
             "p50_latency_ms_per_batch": float(np.median(step_ms)), "p50_latency_ms_single_problem": lat1,
             "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),
             "steady_state": {"value": tot_B * a.steps / (maxs["warm_ms"] * 1e-3), "unit": UNIT, "ms_per_step": maxs["warm_ms"] / a.steps,
@@ -342,6 +435,8 @@ def main():
                                      "(shifted previous solution), device-resident inputs"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_source": "static: profiles/traffic.json, one `ncu --set full` capture of the same kernel, batch and "
+                                           "dimensions (not measured in this run)" if traffic is not None else None,
                          "peak_source": "self-measured register-resident DFMA chains (b2mpc_dfma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 ~37-40 TFLOP/s",
                          "flops_per_launch": fl, "kernel_ms": kern_s * 1e3,
@@ -350,9 +445,16 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "BatchedMpcSolver.solve_host -> b2mpc_solve_host (pinned host buffers)"},
+            "closed_loop": {"value": B * world_size / (maxs["cl_ms"] * 1e-3), "unit": "env-steps/s", "ms_per_control_step": maxs["cl_ms"],
+                            "mean_qp_iter": cl_it, "vs_warm_solve_rate": (maxs["warm_ms"] / a.steps) / maxs["cl_ms"],
+                            "what": "b2mpc_closed_loop: 40 control steps of robot_ocp_problem.py:184-260 per environment enqueued by one "
+                                    "call (3 launches per control step), device Philox noise; per-GPU batch as the headline",
+                            "config1_single_episode_ms_per_control_step": cfg1_ms if rank == 0 else None,
+                            "config1_mean_qp_iter": cfg1_it if rank == 0 else None},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
         }
+        line.update(extra)
         if not a.no_cpu_baseline and world_size == 1:
             cores = os.cpu_count() or 1
             sample = a.cpu_sample or 4096
@@ -366,7 +468,8 @@ def main():
                                               "pthreads over problems; oracle/mpc_oracle.c = CPU restatement of the acados "
                                               "algorithm, not acados (parity unpinned)"}
         print(json.dumps(line), flush=True)
-    solver.close()
+    if a.no_extra_configs:
+        solver.close()
     if world_size > 1:
         dist.destroy_process_group()
 

@@ -50,7 +50,8 @@ EXPORTS = [
     "b2mpc_set_host", "b2mpc_get_host", "b2mpc_get_i32_host", "b2mpc_field_ptr",
     "b2mpc_prepare_slack", "b2mpc_reset", "b2mpc_solve", "b2mpc_sim", "b2mpc_shift",
     "b2mpc_launch_count", "b2mpc_kernel", "b2mpc_solve_host", "b2mpc_dfma_peak",
-    "b2mpc_obst_predict", "b2mpc_loop_reset", "b2mpc_loop_post", "b2mpc_solve_sqp",
+    "b2mpc_obst_predict", "b2mpc_loop_reset", "b2mpc_loop_post", "b2mpc_solve_sqp", "b2mpc_loop_begin",
+    "b2mpc_closed_loop",
 ]
 
 
@@ -88,6 +89,8 @@ def lib():
     L.b2mpc_dfma_peak.argtypes = [C.c_int, dp]
     L.b2mpc_obst_predict.argtypes = [vp, i64, i32, vp]
     L.b2mpc_loop_reset.argtypes = [vp, i64, vp]
+    L.b2mpc_loop_begin.argtypes = [vp, i64, vp]
+    L.b2mpc_closed_loop.argtypes = [vp, i64, i32, i32, C.c_uint64, i64, vp, i32, i32, i32, C.c_double, vp]
     L.b2mpc_loop_post.argtypes = [vp, i64, vp, i32, i32, C.c_double, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -14,10 +14,11 @@ from .solver import BatchedMpcSolver
 class BatchedRobotOcp:
     def __init__(self, robot_init, robot_end, obstacles, dims: world.MpcDims = world.MpcDims(), slack=True,
                  init_guess_when_error=False, random_move=False, noise=None, device=0, quirk_prediction=True,
-                 qp_iter_max=world.QP_ITER, **solver_overrides):
+                 qp_iter_max=world.QP_ITER, seed=0, env_offset=0, **solver_overrides):
         """robot_init [B,5] (or [5]), robot_end [B,2] (or [2]), obstacles [B,M,4] (x,y,vx,vy);
-        noise: optional [steps,B,M,2] N(0,1) stream (reference-identical streams:
-        world.reference_episode_streams); without it torch.randn is used when random_move."""
+        noise: optional [steps,B,M,2] N(0,1) stream to replay (reference-identical streams:
+        world.reference_episode_streams); without it, random_move draws the on-device Philox stream keyed by
+        (seed, env_offset + environment, control step, obstacle) -- the same for any batch size or sharding."""
         import torch
         self.torch = torch
         obstacles = np.asarray(obstacles, np.float64)
@@ -31,6 +32,7 @@ class BatchedRobotOcp:
         self.init_guess_when_error = init_guess_when_error
         self.random_move = random_move
         self.quirk_prediction = quirk_prediction
+        self.seed, self.env_offset = seed, env_offset
         self.solver = BatchedMpcSolver(dims.N, dims.M, dims.tf, max_batch=B, device=device,
                                        qp_iter_max=qp_iter_max, **solver_overrides)
         self.dev = torch.device("cuda", device)
@@ -72,12 +74,32 @@ class BatchedRobotOcp:
     def step(self, max_iter, check_every=8):
         """Run the RTI closed loop for at most max_iter control steps per environment.
         Returns (x_final[B,5], hit[B], reached[B], min_margin[B], dist_to_goal[B], steps[B], out_of_bounds[B])."""
+        self.solver.loop_begin(self.B)          # reached_subgoal = False, out_of_bounds = False, i = 0 (:177-183)
         self.set_initial_guess()
         self.advance(max_iter, check_every)
         return self.outcome()
 
     def advance(self, n_steps, check_every=8):
-        """the `while i < max_iter` loop body (:184-260) n_steps times, without re-initialising the guess"""
+        """the `while i < max_iter` loop body (:184-260) n_steps times, without re-initialising the guess: chunks of
+        `check_every` control steps, each enqueued by ONE call into the library (b2mpc_closed_loop: three launches per control
+        step, no host code in between); the host only looks at the done flags between chunks"""
+        s, B = self.solver, self.B
+        taken = 0
+        while taken < n_steps:
+            n = min(check_every, n_steps - taken)
+            noise = None
+            if self.random_move and self._noise is not None:
+                noise = self._noise[self._step_count:self._step_count + n]
+            s.closed_loop(B, n, noise=noise, seed=self.seed, env_offset=self.env_offset, random_move=self.random_move,
+                          init_guess_when_error=self.init_guess_when_error, quirk=self.quirk_prediction, tol=world.TOL)
+            self._step_count += n
+            taken += n
+            if taken < n_steps and bool(s.get_int("done", B).all()):
+                break
+
+    def advance_stepwise(self, n_steps, check_every=8):
+        """the same loop sequenced from Python, one library call per phase (six launches per control step): what
+        `advance` did before b2mpc_closed_loop existed; kept for tests that look between the phases"""
         s, B, torch = self.solver, self.B, self.torch
         for i in range(n_steps):
             s.obst_predict(B, quirk=self.quirk_prediction)          # parameterize_model(), :186
@@ -85,8 +107,8 @@ class BatchedRobotOcp:
             s.solve(B)                                               # :191-195 (x0 embedding is the 'x0' field)
             noise = None
             if self.random_move:
-                noise = self._noise[self._step_count] if self._noise is not None else \
-                    torch.randn(B, self.dims.M, 2, dtype=torch.float64, device=self.dev)
+                assert self._noise is not None, "advance_stepwise replays a given noise stream"
+                noise = self._noise[self._step_count]
             s.loop_post(B, noise, self.random_move, self.init_guess_when_error, world.TOL)   # :198-260
             self._step_count += 1
             if (i + 1) % check_every == 0 and bool(s.get_int("done", B).all()):

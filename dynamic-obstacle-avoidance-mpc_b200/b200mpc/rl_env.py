@@ -57,7 +57,7 @@ class BatchedMpcEnv:
         B, s = self.B, self.ocp.solver
         action = np.clip(np.asarray(action, np.float64).reshape(B, 2), world.X_MIN_ROBOT, world.X_MAX_ROBOT)
         self.ocp.set_subgoal(action)
-        s.loop_reset(B)                                   # per-action bookkeeping (margins, flags, step counter)
+        s.loop_begin(B)                                   # per-action flags and step counter; the episode's min margin is kept
         self.ocp.advance(self.mpc_steps, check_every=self.mpc_steps)
         state, x0, _ = self._observe()
         margin = s.get("margin", B, host=True)[:, 0]

@@ -146,6 +146,10 @@ class BatchedMpcSolver:
     def loop_reset(self, batch):
         capi.check(capi.lib().b2mpc_loop_reset(self._h, batch, self._stream()))
 
+    def loop_begin(self, batch):
+        """head of RobotOcpProblem.step() (:177-183): clears done / out-of-bounds / step counter, keeps the episode's min margin"""
+        capi.check(capi.lib().b2mpc_loop_begin(self._h, batch, self._stream()))
+
     def loop_post(self, batch, noise=None, random_move=False, init_guess_when_error=True, tol=0.15):
         """everything of one control step after solve(), :198-260; noise: CUDA tensor [B,M,2] ~ N(0,1)."""
         npnt = None
@@ -156,6 +160,24 @@ class BatchedMpcSolver:
             self._keep_noise = noise
         capi.check(capi.lib().b2mpc_loop_post(self._h, batch, npnt, 1 if random_move else 0,
                                               1 if init_guess_when_error else 0, float(tol), self._stream()))
+
+    def closed_loop(self, batch, steps, noise=None, seed=0, env_offset=0, random_move=False, init_guess_when_error=True,
+                    quirk=True, tol=0.15):
+        """`steps` control steps of robot_ocp_problem.py:184-260 for every environment, enqueued by one C call
+        (b2mpc_closed_loop).  noise: CUDA tensor [steps,B,M,2] ~ N(0,1) to replay; without it (and random_move) the
+        on-device Philox stream keyed by (seed, env_offset + environment, control step, obstacle) is used."""
+        mode, npnt = 0, None
+        if random_move:
+            if noise is not None:
+                noise = noise.to(self.torch.float64).contiguous()
+                assert noise.is_cuda and tuple(noise.shape) == (steps, batch, self.M, 2), tuple(noise.shape)
+                mode, npnt = 2, C.c_void_p(noise.data_ptr())
+                self._keep_noise = noise
+            else:
+                mode = 1
+        capi.check(capi.lib().b2mpc_closed_loop(self._h, batch, steps, mode, int(seed) & (2 ** 64 - 1), int(env_offset), npnt,
+                                                1 if random_move else 0, 1 if init_guess_when_error else 0,
+                                                1 if quirk else 0, float(tol), self._stream()))
 
     def solve_host(self, x0, p, yref, zl, Zl, x, u, sl, su):
         """One control step on HOST numpy buffers (batch-first): copies in, solves, copies the iterate

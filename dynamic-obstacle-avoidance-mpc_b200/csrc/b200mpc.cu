@@ -32,6 +32,14 @@ static int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(B2MPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+// Every entry point runs on the handle's device whatever device is current in the calling thread, and leaves the
+// caller's current device as it found it (two handles on two GPUs in one process must not disturb each other).
+struct B2DeviceGuard {
+    int prev = -1, dev;
+    explicit B2DeviceGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+    ~B2DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
 #define B2_ORDER_MAXKEYS 72         // >= number of keys of the launch-order counting sort (B2_ORDER_NKEYS)
 
 struct b2mpc {
@@ -41,10 +49,9 @@ struct b2mpc {
     double* f[B2MPC_N_FIELDS];       // SoA [len][Bm]
     int32_t* fi[B2MPC_N_IFIELDS];    // [Bm]
     double* stage_d;                 // device staging for layout conversion (max field len * Bm)
-    double* stage_h;                 // pinned host staging
-    int32_t* stage_hi;
     size_t stage_elems;
     int64_t launches;
+    int64_t loop_step;               // control steps taken since the last b2mpc_loop_reset (Philox counter of the noise stream)
     int32_t* order;                  // launch order for the warp kernel + 2 counters
     int kernel;                      // resolved: 1 thread-per-problem, 2 warp-per-problem (hybrid layout), 3 warp-per-problem (all shared)
     size_t wpp_smem;
@@ -123,7 +130,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(B2MPC_ENODEV, "no CUDA device: libb200mpc has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(B2MPC_ENODEV, "device %d not present (%d devices)", cfg->device, ndev);
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    B2DeviceGuard guard(cfg->device);
     b2mpc* h = new b2mpc();
     memset((void*)h, 0, sizeof(*h));
     h->cfg = *cfg;
@@ -147,9 +154,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         cudaMemset(h->fi[i], 0, sizeof(int32_t) * h->Bm);
     }
     h->stage_elems = (size_t)maxlen * h->Bm;
-    if (cudaMalloc(&h->stage_d, sizeof(double) * h->stage_elems) != cudaSuccess ||
-        cudaMallocHost(&h->stage_h, sizeof(double) * h->stage_elems) != cudaSuccess ||
-        cudaMallocHost(&h->stage_hi, sizeof(int32_t) * h->Bm) != cudaSuccess) {
+    if (cudaMalloc(&h->stage_d, sizeof(double) * h->stage_elems) != cudaSuccess) {
         b2mpc_destroy(h);
         return fail(B2MPC_ENOMEM, "staging allocation failed");
     }
@@ -185,7 +190,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
         h->wpp_smem_sqp = b2_wpp_smem_bytes(N, M, smask_sqp, true);
         if (h->wpp_smem_sqp > (size_t)max_smem) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "warp kernel needs %zu B > %d B of shared memory", h->wpp_smem, max_smem); }
-        if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 2 * B2_ORDER_MAXKEYS + 4)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
+        if (cudaMalloc(&h->order, sizeof(int32_t) * (2 * (size_t)h->Bm + 4 * B2_ORDER_MAXKEYS + 8)) != cudaSuccess) { b2mpc_destroy(h); return fail(B2MPC_ENOMEM, "cudaMalloc(order) failed"); }
         cudaError_t e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->wpp_fn_sqp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wpp_smem_sqp);
@@ -243,14 +248,12 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
 extern "C" int b2mpc_destroy(b2mpc* h)
 {
     if (!h) return B2MPC_OK;
-    cudaSetDevice(h->cfg.device);
+    B2DeviceGuard guard(h->cfg.device);
     for (int i = 0; i < B2MPC_N_FIELDS; i++) if (h->f[i]) cudaFree(h->f[i]);
     for (int i = 0; i < B2MPC_N_IFIELDS; i++) if (h->fi[i]) cudaFree(h->fi[i]);
     if (h->wpriv) cudaFree(h->wpriv);
     if (h->order) cudaFree(h->order);
     if (h->stage_d) cudaFree(h->stage_d);
-    if (h->stage_h) cudaFreeHost(h->stage_h);
-    if (h->stage_hi) cudaFreeHost(h->stage_hi);
     delete h;
     return B2MPC_OK;
 }
@@ -311,6 +314,7 @@ extern "C" int b2mpc_set(b2mpc* h, int field, const double* dptr, int64_t batch,
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if (field < 0 || field >= B2MPC_N_FIELDS || !dptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
     cudaStream_t st = (cudaStream_t)stream;
     const int len = (int)h->len[field];
@@ -330,6 +334,7 @@ extern "C" int b2mpc_get(b2mpc* h, int field, double* dptr, int64_t batch, int l
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if (field < 0 || field >= B2MPC_N_FIELDS || !dptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
     cudaStream_t st = (cudaStream_t)stream;
     const int len = (int)h->len[field];
@@ -349,17 +354,22 @@ extern "C" int b2mpc_get_i32(b2mpc* h, int ifield, int32_t* dptr, int64_t batch,
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if (ifield < 0 || ifield >= B2MPC_N_IFIELDS || !dptr) return fail(B2MPC_EINVAL, "bad int field %d or null pointer", ifield);
     CUDA_TRY(cudaMemcpyAsync(dptr, h->fi[ifield], sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return B2MPC_OK;
 }
 
-// host variants: batch-first host memory <-> SoA device fields through the device staging buffer.
-// The async H2D from pageable memory is staged by the driver; pass pinned memory for full overlap.
+// host variants: batch-first host memory <-> SoA device fields.  The copy goes straight between the caller's buffer and
+// the handle's DEVICE staging buffer (cudaMemcpyAsync on `stream`), then a layout kernel.  b2mpc_set_host does not
+// synchronise: with pinned host memory the copy is truly asynchronous and the caller must keep the buffer alive and
+// unchanged until the stream has passed it (pageable memory is staged by the driver before the call returns).  The
+// get_* variants synchronise the stream before returning.
 extern "C" int b2mpc_set_host(b2mpc* h, int field, const double* hptr, int64_t batch, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if (field < 0 || field >= B2MPC_N_FIELDS || !hptr) return fail(B2MPC_EINVAL, "bad field %d or null pointer", field);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->len[field] * batch;
@@ -371,6 +381,7 @@ extern "C" int b2mpc_get_host(b2mpc* h, int field, double* hptr, int64_t batch, 
     int rc = b2mpc_get(h, field, h ? h->stage_d : nullptr, batch, B2MPC_LAYOUT_AOS, stream);
     if (rc) return rc;
     if (!hptr) return fail(B2MPC_EINVAL, "null pointer");
+    B2DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->len[field] * batch;
     CUDA_TRY(cudaMemcpyAsync(hptr, h->stage_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -381,6 +392,7 @@ extern "C" int b2mpc_get_i32_host(b2mpc* h, int ifield, int32_t* hptr, int64_t b
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if (ifield < 0 || ifield >= B2MPC_N_IFIELDS || !hptr) return fail(B2MPC_EINVAL, "bad int field %d or null pointer", ifield);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(hptr, h->fi[ifield], sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
@@ -390,11 +402,9 @@ extern "C" int b2mpc_get_i32_host(b2mpc* h, int ifield, int32_t* hptr, int64_t b
 
 // ------------------------------------------------------------------ glue kernels
 // parameterize_slack(), robot_ocp_problem.py:145-152
-__global__ void b2_prepare_slack(const double* __restrict__ X0, const double* __restrict__ GOAL, double* __restrict__ ZL,
-                                 double* __restrict__ ZZL, int N, int M, int B, int Bm)
+__device__ __forceinline__ void b2_slack_one(const double* __restrict__ X0, const double* __restrict__ GOAL, double* __restrict__ ZL,
+                                             double* __restrict__ ZZL, int N, int M, int b, int Bm)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
     const double d0 = X0[0 * (size_t)Bm + b] - GOAL[0 * (size_t)Bm + b], d1 = X0[1 * (size_t)Bm + b] - GOAL[1 * (size_t)Bm + b];
     const double v = X0[3 * (size_t)Bm + b], w = X0[4 * (size_t)Bm + b];
     const double scale = 1e4 * (d0 * d0 + d1 * d1 + v * v + w * w + 50.0);
@@ -405,6 +415,13 @@ __global__ void b2_prepare_slack(const double* __restrict__ X0, const double* __
             ZZL[((size_t)i * M + j) * Bm + b] = a;
         }
     }
+}
+__global__ void b2_prepare_slack(const double* __restrict__ X0, const double* __restrict__ GOAL, double* __restrict__ ZL,
+                                 double* __restrict__ ZZL, int N, int M, int B, int Bm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    b2_slack_one(X0, GOAL, ZL, ZZL, N, M, b, Bm);
 }
 // ocp_solver.reset() + set_initial_guess(), robot_ocp_problem.py:286-306 (incl. aliasing quirk :301-302)
 __global__ void b2_reset(double* __restrict__ X0, double* __restrict__ X, double* __restrict__ U, double* __restrict__ SL,
@@ -455,6 +472,7 @@ extern "C" int b2mpc_prepare_slack(b2mpc* h, int64_t batch, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     b2_prepare_slack<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         h->f[B2MPC_X0], h->f[B2MPC_GOAL], h->f[B2MPC_ZL], h->f[B2MPC_ZZL], h->N, h->M, (int)batch, h->Bm);
     h->launches++;
@@ -465,6 +483,7 @@ extern "C" int b2mpc_reset(b2mpc* h, const uint8_t* dmask, int64_t batch, void* 
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     b2_reset<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         h->f[B2MPC_X0], h->f[B2MPC_X], h->f[B2MPC_U], h->f[B2MPC_SL], h->f[B2MPC_SU], h->f[B2MPC_PI], h->f[B2MPC_LAM], h->f[B2MPC_T],
         dmask, h->N, h->M, (int)batch, h->Bm);
@@ -476,6 +495,7 @@ extern "C" int b2mpc_sim(b2mpc* h, int64_t batch, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     b2_sim<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         h->f[B2MPC_X0], h->f[B2MPC_U], h->prm.dt, h->cfg.integrator, (int)batch, h->Bm);
     h->launches++;
@@ -486,6 +506,7 @@ extern "C" int b2mpc_shift(b2mpc* h, int64_t batch, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     b2_shift<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->f[B2MPC_X], h->f[B2MPC_U], h->N, (int)batch, h->Bm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -520,13 +541,9 @@ __device__ __forceinline__ void b2_obst_move(double& x, double& vx, double& y, d
 }
 
 // parameterize_model(): one thread per (problem, obstacle), robot_ocp_problem.py:154-166
-__global__ void b2_obst_predict(const double* __restrict__ OBST, double* __restrict__ P, const int32_t* __restrict__ DONE,
-                                int N, int M, double dt, int quirk, int B, int Bm)
+__device__ __forceinline__ void b2_predict_one(const double* __restrict__ OBST, double* __restrict__ P, int N, int M, double dt,
+                                               int quirk, int b, int j, int Bm)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = t % B, j = t / B;
-    if (j >= M) return;
-    if (DONE[b]) return;
     double x = OBST[((size_t)j * 4 + 0) * Bm + b], y = OBST[((size_t)j * 4 + 1) * Bm + b];
     double vy = OBST[((size_t)j * 4 + 3) * Bm + b];
     double vx = quirk ? vy : OBST[((size_t)j * 4 + 2) * Bm + b];        // `vx = self.vy`, visualization.py:69
@@ -535,6 +552,15 @@ __global__ void b2_obst_predict(const double* __restrict__ OBST, double* __restr
         b2_obst_move(x, vx, y, vy, dt);
         P[((size_t)(i + 1) * 2 * M + 2 * j) * Bm + b] = x; P[((size_t)(i + 1) * 2 * M + 2 * j + 1) * Bm + b] = y;
     }
+}
+__global__ void b2_obst_predict(const double* __restrict__ OBST, double* __restrict__ P, const int32_t* __restrict__ DONE,
+                                int N, int M, double dt, int quirk, int B, int Bm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = t % B, j = t / B;
+    if (j >= M) return;
+    if (DONE[b]) return;
+    b2_predict_one(OBST, P, N, M, dt, quirk, b, j, Bm);
 }
 
 __global__ void b2_loop_reset(double* __restrict__ MARGIN, int32_t* STEPS, int32_t* DONE, int32_t* OOB, int32_t* NFAIL, int B, int Bm)
@@ -545,14 +571,56 @@ __global__ void b2_loop_reset(double* __restrict__ MARGIN, int32_t* STEPS, int32
     STEPS[b] = 0; DONE[b] = 0; OOB[b] = 0; NFAIL[b] = 0;
 }
 
-// robot_ocp_problem.py:198-260 for one problem per thread
-__global__ void b2_loop_post(B2Params p, double* __restrict__ X0w, const double* __restrict__ GOAL, double* __restrict__ OBST,
-                             double* __restrict__ MARGIN, double* __restrict__ U0, int32_t* STEPS, int32_t* DONE, int32_t* OOB,
-                             int32_t* NFAIL, const double* __restrict__ noise, int random_move, int init_guess_when_error, double tol)
+// head of RobotOcpProblem.step() (robot_ocp_problem.py:177-183): reached_subgoal = False, out_of_bounds = False, i = 0;
+// min_margin_traj belongs to the experiment (init_experiment, :51) and survives
+__global__ void b2_loop_begin(int32_t* STEPS, int32_t* DONE, int32_t* OOB, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
-    if (DONE[b]) return;
+    if (b >= B) return;
+    STEPS[b] = 0; DONE[b] = 0; OOB[b] = 0;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11: the counter-based generator behind cuRAND's and numpy's Philox), written out so
+// that the velocity-noise stream of an environment (visualization.py:28-33: np.random.normal per obstacle and control step)
+// depends only on (seed, GLOBAL environment index, control step, obstacle) -- never on the batch or the shard it runs in.
+__host__ __device__ __forceinline__ void b2_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two independent N(0,1) draws for (environment, control step, obstacle): Box-Muller on two 53-bit uniforms in (0,1)
+__device__ __forceinline__ void b2_philox_normal2(uint64_t seed, uint64_t env, uint32_t step, uint32_t obstacle, double* n0, double* n1)
+{
+    uint32_t r[4];
+    b2_philox4x32_10(step, obstacle, (uint32_t)env, (uint32_t)(env >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    *n0 = rad * cs; *n1 = rad * sn;
+}
+
+// where the velocity noise of the closed loop comes from
+struct B2Noise {
+    int mode;                 // 0 none, 1 device Philox stream, 2 replay of a caller-provided stream
+    const double* replay;     // mode 2: [batch][M][2] for THIS control step (batch-first)
+    uint64_t seed;            // mode 1
+    int64_t env_offset;       //         global index of environment 0 of this batch (shards draw the unsharded run's streams)
+    uint32_t step;            //         control-step counter of the experiment
+};
+
+// robot_ocp_problem.py:198-260 for one problem
+__device__ __forceinline__ void b2_post_one(const B2Params& p, int b, double* __restrict__ X0w, const double* __restrict__ GOAL,
+                                            double* __restrict__ OBST, double* __restrict__ MARGIN, double* __restrict__ U0,
+                                            int32_t* STEPS, int32_t* DONE, int32_t* OOB, int32_t* NFAIL, const B2Noise& nz,
+                                            int random_move, int init_guess_when_error, double tol)
+{
     const size_t Bm = (size_t)p.Bm;
     const int N = p.N, M = p.M;
     // u = ocp_solver.get(0,'u') (:198): on status 4 acados left the iterate untouched -> stale u0
@@ -582,8 +650,10 @@ __global__ void b2_loop_post(B2Params p, double* __restrict__ X0w, const double*
     for (int j = 0; j < M; j++) {
         double ox = OBST[((size_t)j * 4 + 0) * Bm + b], oy = OBST[((size_t)j * 4 + 1) * Bm + b];
         double vx = OBST[((size_t)j * 4 + 2) * Bm + b], vy = OBST[((size_t)j * 4 + 3) * Bm + b];
-        if (random_move && noise) {
-            const double n0 = noise[((size_t)b * M + j) * 2 + 0], n1 = noise[((size_t)b * M + j) * 2 + 1];
+        if (random_move && nz.mode) {
+            double n0, n1;
+            if (nz.mode == 2) { n0 = nz.replay[((size_t)b * M + j) * 2 + 0]; n1 = nz.replay[((size_t)b * M + j) * 2 + 1]; }
+            else b2_philox_normal2(nz.seed, (uint64_t)(nz.env_offset + b), nz.step, (uint32_t)j, &n0, &n1);
             vx = fmin(fmax((1.0 + B2_RANDOMNESS * n0) * vx, -B2_V_MAX_OBST), B2_V_MAX_OBST);   // visualization.py:28-33
             vy = fmin(fmax((1.0 + B2_RANDOMNESS * n1) * vy, -B2_V_MAX_OBST), B2_V_MAX_OBST);
         }
@@ -608,11 +678,22 @@ __global__ void b2_loop_post(B2Params p, double* __restrict__ X0w, const double*
     p.U[((size_t)(N - 1) * 2) * Bm + b] = 0.0; p.U[((size_t)(N - 1) * 2 + 1) * Bm + b] = 0.0;
     STEPS[b] += 1;
 }
+__global__ void b2_loop_post(B2Params p, double* __restrict__ X0w, const double* __restrict__ GOAL, double* __restrict__ OBST,
+                             double* __restrict__ MARGIN, double* __restrict__ U0, int32_t* STEPS, int32_t* DONE, int32_t* OOB,
+                             int32_t* NFAIL, B2Noise nz, int random_move, int init_guess_when_error, double tol)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    if (DONE[b]) return;
+    b2_post_one(p, b, X0w, GOAL, OBST, MARGIN, U0, STEPS, DONE, OOB, NFAIL, nz, random_move, init_guess_when_error, tol);
+}
+
 
 extern "C" int b2mpc_obst_predict(b2mpc* h, int64_t batch, int32_t quirk, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     const int64_t n = batch * h->M;
     b2_obst_predict<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         h->f[B2MPC_OBST], h->f[B2MPC_P], h->fi[B2MPC_DONE], h->N, h->M, h->prm.dt, quirk, (int)batch, h->Bm);
@@ -624,8 +705,21 @@ extern "C" int b2mpc_loop_reset(b2mpc* h, int64_t batch, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     b2_loop_reset<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         h->f[B2MPC_MARGIN], h->fi[B2MPC_STEPS], h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], h->fi[B2MPC_NFAIL], (int)batch, h->Bm);
+    h->loop_step = 0;
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+extern "C" int b2mpc_loop_begin(b2mpc* h, int64_t batch, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
+    b2_loop_begin<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->fi[B2MPC_STEPS], h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], (int)batch);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;
@@ -635,11 +729,13 @@ extern "C" int b2mpc_loop_post(b2mpc* h, int64_t batch, const double* dnoise, in
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     B2Params p = h->prm;
     p.B = (int)batch;
     b2_loop_post<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         p, h->f[B2MPC_X0], h->f[B2MPC_GOAL], h->f[B2MPC_OBST], h->f[B2MPC_MARGIN], h->f[B2MPC_U0], h->fi[B2MPC_STEPS],
-        h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], h->fi[B2MPC_NFAIL], dnoise, random_move, init_guess_when_error, tol);
+        h->fi[B2MPC_DONE], h->fi[B2MPC_OOB], h->fi[B2MPC_NFAIL], B2Noise{dnoise ? 2 : 0, dnoise, 0, 0, 0}, random_move,
+        init_guess_when_error, tol);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;
@@ -653,11 +749,8 @@ extern "C" int b2mpc_loop_post(b2mpc* h, int64_t batch, const double* dnoise, in
 // count 0.84.  Counting sort by that key, expensive first.  Pure scheduling: per-problem results are unaffected.
 #define B2_ORDER_NODEKEYS 64
 #define B2_ORDER_NKEYS (B2_ORDER_NODEKEYS + 3)
-__global__ void b2_order_keys(const double* __restrict__ X, const double* __restrict__ P, int32_t* __restrict__ key,
-                              int32_t* __restrict__ hist, int N, int M, double r2, int B, int Bm)
+__device__ __forceinline__ int b2_order_key_one(const double* __restrict__ X, const double* __restrict__ P, int N, int M, double r2, int b, int Bm)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
     int first = -1;
     double hmin = 1e300;
     for (int k = 0; k <= N && first < 0; k++) {
@@ -669,27 +762,124 @@ __global__ void b2_order_keys(const double* __restrict__ X, const double* __rest
             if (h < 0.0) first = k;
         }
     }
-    const int kk = first >= 0 ? (first < B2_ORDER_NODEKEYS ? first : B2_ORDER_NODEKEYS - 1)
-                              : B2_ORDER_NODEKEYS + (hmin < 1.0 ? 0 : (hmin < 3.0 ? 1 : 2));
-    key[b] = kk;
-    atomicAdd(&hist[kk], 1);
+    return first >= 0 ? (first < B2_ORDER_NODEKEYS ? first : B2_ORDER_NODEKEYS - 1)
+                      : B2_ORDER_NODEKEYS + (hmin < 1.0 ? 0 : (hmin < 3.0 ? 1 : 2));
 }
-__global__ void b2_order_scatter(const int32_t* __restrict__ key, const int32_t* __restrict__ hist, int32_t* __restrict__ fill,
-                                 int32_t* __restrict__ order, int nkeys, int B)
+__global__ void b2_order_keys(const double* __restrict__ X, const double* __restrict__ P, int32_t* __restrict__ key,
+                              int32_t* __restrict__ hist, int N, int M, double r2, int B, int Bm)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int kk = b2_order_key_one(X, P, N, M, r2, b, Bm);
+    key[b] = kk;
+    atomicAdd(&hist[kk], 1);
+}
+// key < 0: the problem is not queued (closed loop: an environment that has reached its goal).  The first thread also
+// prepares what the persistent solve kernel and the NEXT scatter need: work counter, queue length, and -- the key
+// histogram being double-buffered between control steps -- zeroes of the other buffer.
+__global__ void b2_order_scatter(const int32_t* __restrict__ key, const int32_t* __restrict__ hist, int32_t* __restrict__ fill,
+                                 int32_t* __restrict__ order, int nkeys, int B, int32_t* next, int32_t* nqueue,
+                                 int32_t* other_hist, int32_t* other_fill)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) {
+        if (next) *next = 0;
+        if (nqueue) { int tot = 0; for (int c = 0; c < nkeys; c++) tot += hist[c]; *nqueue = tot; }
+    }
+    if (other_hist && b < nkeys) { other_hist[b] = 0; other_fill[b] = 0; }
+    if (b >= B) return;
     const int kk = key[b];
+    if (kk < 0) return;
     int start = 0;
     for (int c = 0; c < kk; c++) start += hist[c];
     order[start + atomicAdd(&fill[kk], 1)] = b;
 }
 
+// ---- the fused closed loop (b2mpc_closed_loop): everything of robot_ocp_problem.py:184-260 that is not the solve, for one
+// environment per thread, in ONE kernel between two solves: the rest of control step i (b2_post_one: u0, failure handling,
+// plant step, obstacle step with noise, margins, goal test, shift) and the head of step i+1 (parameterize_model,
+// parameterize_slack, queue key).  Environments that reached their goal leave the queue: the solve kernel only sees the
+// active ones.  Queue key of a warm-started problem: the interior-point iteration count of its previous solve (already on
+// the device; expensive first), of a fresh one: the geometric predictor of b2_order_key_one.
+struct B2LoopArgs {
+    double *X0w, *GOAL, *OBST, *MARGIN, *U0;
+    int32_t *STEPS, *DONE, *OOB, *NFAIL;
+    B2Noise nz;
+    int random_move, init_guess_when_error, quirk, do_post, do_pre;
+    double tol;
+    int32_t *key, *hist;
+};
+__global__ void b2_loop_glue(B2Params p, B2LoopArgs a)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    bool fresh = !a.do_post;
+    if (a.do_post && !a.DONE[b]) {
+        fresh = p.STATUS[b] == 4 && a.init_guess_when_error;       // re-initialised iterate: the previous count says nothing
+        b2_post_one(p, b, a.X0w, a.GOAL, a.OBST, a.MARGIN, a.U0, a.STEPS, a.DONE, a.OOB, a.NFAIL, a.nz, a.random_move,
+                    a.init_guess_when_error, a.tol);
+    }
+    if (!a.do_pre) return;
+    if (a.DONE[b]) { a.key[b] = -1; return; }
+    for (int j = 0; j < p.M; j++) b2_predict_one(a.OBST, const_cast<double*>(p.P), p.N, p.M, p.dt, a.quirk, b, j, p.Bm);
+    b2_slack_one(a.X0w, a.GOAL, const_cast<double*>(p.ZL), const_cast<double*>(p.ZZL), p.N, p.M, b, p.Bm);
+    const int it = p.QP_ITER[b];
+    int kk;
+    if (!fresh && it > 0) kk = B2_ORDER_NODEKEYS - 1 - (it < B2_ORDER_NODEKEYS ? it : B2_ORDER_NODEKEYS - 1);
+    else kk = b2_order_key_one(p.X, p.P, p.N, p.M, p.r2, b, p.Bm);
+    a.key[b] = kk;
+    atomicAdd(&a.hist[kk], 1);
+}
+
 // ------------------------------------------------------------------ the solve
+// order buffer of a handle: [order (Bm) | key (Bm) | hist0 | fill0 | hist1 | fill1 (MAXKEYS each) | work counter | queue length]
+struct B2Order {
+    int32_t *order, *key, *hist[2], *fill[2], *next, *nq;
+    explicit B2Order(b2mpc* h)
+    {
+        order = h->order; key = order + h->Bm;
+        hist[0] = key + h->Bm; fill[0] = hist[0] + B2_ORDER_MAXKEYS;
+        hist[1] = fill[0] + B2_ORDER_MAXKEYS; fill[1] = hist[1] + B2_ORDER_MAXKEYS;
+        next = fill[1] + B2_ORDER_MAXKEYS; nq = next + 1;
+    }
+};
+
+// launch the solve kernel on a prepared queue (p.ORDER / p.NEXT / p.NQ set by the caller)
+static int launch_solve(b2mpc* h, B2Params& p, int64_t batch, bool sqp, cudaStream_t st)
+{
+    if (sqp) {
+        const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);
+        p.wpriv_stride = h->wpriv_stride_sqp;
+        h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem_sqp, st>>>(p);
+    } else if (h->wpp_fn_small && batch <= h->small_batch_max) {
+        h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
+    } else {
+        const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);   // persistent: one warp-CTA per resident slot
+        if (h->l2_persist && h->wpriv_bytes) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(blocks); lc.blockDim = dim3(32); lc.dynamicSmemBytes = h->wpp_smem; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            at[0].val.accessPolicyWindow.base_ptr = h->wpriv;
+            at[0].val.accessPolicyWindow.num_bytes = sizeof(double) * h->prm.wpriv_stride * (size_t)blocks;
+            at[0].val.accessPolicyWindow.hitRatio = h->l2_hit_ratio;
+            at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            lc.attrs = at; lc.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&lc, h->wpp_fn, (const B2Params)p));
+        } else
+        h->wpp_fn<<<blocks, 32, h->wpp_smem, st>>>(p);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2MPC_OK;
+}
+
 static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const double* tol4, void* stream)
 {
     int rc = check_batch(h, batch);
     if (rc) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     B2Params p = h->prm;
     p.B = (int)batch;
@@ -697,44 +887,65 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
         if (max_iter > 0) p.nlp_iter_max = max_iter;
         if (tol4) for (int i = 0; i < 4; i++) p.nlp_tol[i] = tol4[i];
     }
-    {
-        // order buffer: [order (Bm) | key (Bm) | hist (MAXKEYS) | fill (MAXKEYS) | work counter]
-        int32_t* key = h->order + h->Bm;
-        int32_t* hist = key + h->Bm;
-        int32_t* fill = hist + B2_ORDER_MAXKEYS;
-        int32_t* next = fill + B2_ORDER_MAXKEYS;
-        CUDA_TRY(cudaMemsetAsync(hist, 0, (2 * B2_ORDER_MAXKEYS + 4) * sizeof(int32_t), st));
-        const unsigned ob = (unsigned)((batch + 127) / 128);
-        b2_order_keys<<<ob, 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], key, hist, h->N, h->M, h->cfg.r2, (int)batch, h->Bm);
-        b2_order_scatter<<<ob, 128, 0, st>>>(key, hist, fill, h->order, B2_ORDER_NKEYS, (int)batch);
-        h->launches += 2;
-        p.ORDER = h->order;
-        p.NEXT = next;
-        if (sqp) {
-            const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);
-            p.wpriv_stride = h->wpriv_stride_sqp;
-            h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem_sqp, st>>>(p);
-        } else if (h->wpp_fn_small && batch <= h->small_batch_max) {
-            h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
-        } else {
-            const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);   // persistent: one warp-CTA per resident slot
-            if (h->l2_persist && h->wpriv_bytes) {
-                cudaLaunchConfig_t lc = {};
-                lc.gridDim = dim3(blocks); lc.blockDim = dim3(32); lc.dynamicSmemBytes = h->wpp_smem; lc.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-                at[0].val.accessPolicyWindow.base_ptr = h->wpriv;
-                at[0].val.accessPolicyWindow.num_bytes = sizeof(double) * h->prm.wpriv_stride * (size_t)blocks;
-                at[0].val.accessPolicyWindow.hitRatio = h->l2_hit_ratio;
-                at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                lc.attrs = at; lc.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&lc, h->wpp_fn, (const B2Params)p));
-            } else
-            h->wpp_fn<<<blocks, 32, h->wpp_smem, st>>>(p);
-        }
-    }
+    B2Order o(h);
+    CUDA_TRY(cudaMemsetAsync(o.hist[0], 0, (4 * B2_ORDER_MAXKEYS + 8) * sizeof(int32_t), st));
+    const unsigned ob = (unsigned)((batch + 127) / 128);
+    b2_order_keys<<<ob, 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], o.key, o.hist[0], h->N, h->M, h->cfg.r2, (int)batch, h->Bm);
+    b2_order_scatter<<<ob, 128, 0, st>>>(o.key, o.hist[0], o.fill[0], o.order, B2_ORDER_NKEYS, (int)batch, nullptr, nullptr, nullptr, nullptr);
+    h->launches += 2;
+    p.ORDER = o.order;
+    p.NEXT = o.next;
+    p.NQ = nullptr;
+    return launch_solve(h, p, batch, sqp, st);
+}
+
+// RobotOcpProblem.step()'s `while i < max_iter` loop (robot_ocp_problem.py:184-260) for `steps` control steps, enqueued by ONE
+// call: per control step three launches -- queue scatter, solve, glue (rest of this step + head of the next) -- instead of
+// six launches and a trip through the host language.
+extern "C" int b2mpc_closed_loop(b2mpc* h, int64_t batch, int32_t steps, int32_t noise_mode, uint64_t seed, int64_t env_offset,
+                                 const double* dnoise, int32_t random_move, int32_t init_guess_when_error, int32_t quirk_vx_is_vy,
+                                 double tol, void* stream)
+{
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    if (steps < 0) return fail(B2MPC_EINVAL, "steps must be >= 0");
+    if (noise_mode < 0 || noise_mode > 2) return fail(B2MPC_EINVAL, "noise_mode must be 0 (none), 1 (device Philox stream) or 2 (replay)");
+    if (noise_mode == 2 && !dnoise) return fail(B2MPC_EINVAL, "noise_mode 2 needs a device noise stream [steps][batch][M][2]");
+    if (h->cfg.nlp_solver == 1) return fail(B2MPC_EINVAL, "the closed loop is the reference's SQP_RTI loop (cfg.nlp_solver = 0)");
+    if (steps == 0) return B2MPC_OK;
+    B2DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    B2Params p = h->prm;
+    p.B = (int)batch;
+    B2Order o(h);
+    CUDA_TRY(cudaMemsetAsync(o.hist[0], 0, (4 * B2_ORDER_MAXKEYS + 8) * sizeof(int32_t), st));
+    B2LoopArgs a;
+    a.X0w = h->f[B2MPC_X0]; a.GOAL = h->f[B2MPC_GOAL]; a.OBST = h->f[B2MPC_OBST]; a.MARGIN = h->f[B2MPC_MARGIN]; a.U0 = h->f[B2MPC_U0];
+    a.STEPS = h->fi[B2MPC_STEPS]; a.DONE = h->fi[B2MPC_DONE]; a.OOB = h->fi[B2MPC_OOB]; a.NFAIL = h->fi[B2MPC_NFAIL];
+    a.random_move = random_move; a.init_guess_when_error = init_guess_when_error; a.quirk = quirk_vx_is_vy; a.tol = tol;
+    a.key = o.key;
+    const unsigned ob = (unsigned)((batch + 127) / 128);
+    const size_t noise_stride = (size_t)batch * h->M * 2;
+    int cur = 0;
+    // head of the first control step
+    a.do_post = 0; a.do_pre = 1; a.hist = o.hist[cur];
+    a.nz = B2Noise{0, nullptr, 0, 0, 0};
+    b2_loop_glue<<<ob, 128, 0, st>>>(p, a);
     h->launches++;
+    for (int i = 0; i < steps; i++) {
+        b2_order_scatter<<<ob, 128, 0, st>>>(o.key, o.hist[cur], o.fill[cur], o.order, B2_ORDER_NKEYS, (int)batch, o.next, o.nq,
+                                             o.hist[cur ^ 1], o.fill[cur ^ 1]);
+        h->launches++;
+        p.ORDER = o.order; p.NEXT = o.next; p.NQ = o.nq;
+        if ((rc = launch_solve(h, p, batch, false, st))) return rc;
+        cur ^= 1;
+        a.do_post = 1; a.do_pre = (i + 1 < steps) ? 1 : 0; a.hist = o.hist[cur];
+        a.nz = B2Noise{random_move ? noise_mode : 0, noise_mode == 2 ? dnoise + (size_t)i * noise_stride : nullptr, seed, env_offset,
+                       (uint32_t)(h->loop_step + i)};
+        b2_loop_glue<<<ob, 128, 0, st>>>(p, a);
+        h->launches++;
+    }
+    h->loop_step += steps;
     CUDA_TRY(cudaGetLastError());
     return B2MPC_OK;
 }
@@ -755,6 +966,8 @@ extern "C" int b2mpc_solve_host(b2mpc* h, int64_t batch, const double* x0, const
 {
     int rc;
     if (!x0 || !p || !yref || !zl || !Zl || !x || !u || !sl || !su) return fail(B2MPC_EINVAL, "null pointer");
+    if ((rc = check_batch(h, batch))) return rc;
+    B2DeviceGuard guard(h->cfg.device);
     if ((rc = b2mpc_set_host(h, B2MPC_X0, x0, batch, stream))) return rc;
     if ((rc = b2mpc_set_host(h, B2MPC_P, p, batch, stream))) return rc;
     if ((rc = b2mpc_set_host(h, B2MPC_YREF, yref, batch, stream))) return rc;
@@ -801,7 +1014,7 @@ extern "C" int b2mpc_dfma_peak(int device, double* tflops_out)
     if (!tflops_out) return fail(B2MPC_EINVAL, "null pointer");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B2MPC_ENODEV, "no such CUDA device %d", device);
-    CUDA_TRY(cudaSetDevice(device));
+    B2DeviceGuard guard(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;

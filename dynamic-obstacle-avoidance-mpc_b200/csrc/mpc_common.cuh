@@ -75,6 +75,7 @@ struct B2Params {
     int32_t* SQP_ITER;
     const int32_t* ORDER;        // optional launch order of the problems (warp kernel)
     int32_t* NEXT;               // work counter of the persistent warp kernel (zeroed before each launch)
+    const int32_t* NQ;           // optional: length of the queue ORDER (closed loop: finished environments are not queued); NULL: B
     // scratch
     double* WPRIV;               // warp kernel: node-private rows, one block of wpriv_stride doubles per resident CTA
     size_t wpriv_stride;

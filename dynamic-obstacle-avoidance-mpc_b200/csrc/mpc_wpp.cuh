@@ -1303,14 +1303,15 @@ struct WppSolver {
                     p.SL[((size_t)k * M + j) * Bm + b] += Q<PF_SL>(j);
                     p.SU[((size_t)k * M + j) * Bm + b] += Q<PF_SU>(j);
                 }
-            }
-            if (k < N) {
+                // multipliers <- QP multipliers; like the primal iterate they stay untouched on ACADOS_QP_FAILURE
+                if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = PP(i, k);
-            }
-            for (int i = 0; i < nct; i++) {
-                p.LAM[((size_t)k * nct + i) * Bm + b] = Q<PF_LAM>(i);
-                p.T[((size_t)k * nct + i) * Bm + b] = Q<PF_T>(i);
+                    for (int i = 0; i < 5; i++) p.PI[((size_t)k * 5 + i) * Bm + b] = PP(i, k);
+                }
+                for (int i = 0; i < nct; i++) {
+                    p.LAM[((size_t)k * nct + i) * Bm + b] = Q<PF_LAM>(i);
+                    p.T[((size_t)k * nct + i) * Bm + b] = Q<PF_T>(i);
+                }
             }
         }
         sqp_it++;
@@ -1341,11 +1342,12 @@ __global__ void B2_WPP_BOUNDS(NT, SMASK) b2_rti_solve_wpp(const B2Params p)
 {
     B2_DYNAMIC_SMEM(double, b2_smem);
     double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows
+    const int nq = p.NQ ? *p.NQ : p.B;
     for (;;) {
         int i = 0;
         if ((threadIdx.x & 31) == 0) i = atomicAdd(p.NEXT, 1);
         i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= p.B) break;
+        if (i >= nq) break;
         const int b = p.ORDER ? p.ORDER[i] : i;      // expensive problems first (shorter tail), see b2_order_problems
         WppSolver<MT, NT, SMASK, SQP> s(p, b, b2_smem, gm);
         s.run();

@@ -13,7 +13,12 @@
  *   - device arrays are FP64, contiguous, "batch-last" structure-of-arrays: field[len][batch]
  *     (B2MPC_LAYOUT_SOA), or batch-first field[batch][len] (B2MPC_LAYOUT_AOS, transposed on
  *     device).  Host variants (`*_host`) take batch-first host memory (what numpy users hold)
- *     and do the H2D/D2H copies on `stream` through the handle's pinned staging buffers.
+ *     and copy on `stream` straight between the caller's buffer and a device staging buffer of the
+ *     handle.  b2mpc_set_host does NOT synchronise: a pinned source buffer must stay alive and unchanged
+ *     until the stream has passed the copy; the get_*_host variants and b2mpc_solve_host synchronise.
+ *   - every entry point runs on the handle's device (cfg.device) whatever device is current in the
+ *     calling thread and restores the caller's current device before returning: handles on different
+ *     GPUs can be used from one thread.
  *   - the handle owns all device memory (sized by max_batch at create; no allocation later);
  *     callers own what they pass; pointers are borrowed for the stream-ordered call only.
  *   - every function returns 0 on success or a negative B2MPC_E* code, message via
@@ -160,12 +165,30 @@ int b2mpc_shift(b2mpc *h, int64_t batch, void *stream);
 int b2mpc_obst_predict(b2mpc *h, int64_t batch, int32_t quirk_vx_is_vy, void *stream);
 /* zero the closed-loop bookkeeping (init_experiment, :35-52) */
 int b2mpc_loop_reset(b2mpc *h, int64_t batch, void *stream);
+/* head of RobotOcpProblem.step(), :177-183: reached_subgoal = False, out_of_bounds = False, i = 0 -- clears DONE, OOB
+ * and STEPS so that set_subgoal() followed by step() moves an environment that had reached its previous sub-goal;
+ * the episode's min_margin_traj (MARGIN[0]) and NFAIL are kept */
+int b2mpc_loop_begin(b2mpc *h, int64_t batch, void *stream);
 /* the rest of one control step after b2mpc_solve, :198-260: read u0, on status 4 re-initialise the
  * guess (init_guess_when_error, incl. the x0 aliasing quirk), plant step, out-of-bounds flag, obstacle
  * step with noise[batch][M][2] ~ N(0,1) (device, batch-first; NULL or random_move=0: no noise),
  * margins, goal test with tolerance `tol`, warm-start shift.  Finished problems are frozen. */
 int b2mpc_loop_post(b2mpc *h, int64_t batch, const double *dnoise, int32_t random_move,
                     int32_t init_guess_when_error, double tol, void *stream);
+
+/* The whole `while i < max_iter` loop of RobotOcpProblem.step() (robot_ocp_problem.py:184-260) for `steps` control steps of
+ * every environment, enqueued on `stream` by ONE call (per control step: queue scatter, solve, and one glue kernel that
+ * finishes the step -- b2mpc_loop_post -- and starts the next -- b2mpc_obst_predict + b2mpc_prepare_slack).  Environments
+ * that have reached their goal leave the queue.  Velocity noise of the obstacles (visualization.py:28-33):
+ *   noise_mode 0  none;
+ *   noise_mode 1  on-device Philox4x32-10 + Box-Muller stream keyed by (seed, env_offset + environment, control step since
+ *                 the last b2mpc_loop_reset, obstacle): the same for any batch size or sharding of the environments;
+ *   noise_mode 2  replay of dnoise[steps][batch][M][2] ~ N(0,1) (device, batch-first), e.g. the streams
+ *                 `np.random.seed(i)` gives the reference's episodes.
+ * random_move = 0 switches the noise off whatever the mode.  Does not synchronise. */
+int b2mpc_closed_loop(b2mpc *h, int64_t batch, int32_t steps, int32_t noise_mode, uint64_t seed, int64_t env_offset,
+                      const double *dnoise, int32_t random_move, int32_t init_guess_when_error,
+                      int32_t quirk_vx_is_vy, double tol, void *stream);
 
 /* which solve kernel the handle resolved to: 2 = warp-per-problem (node-private rows in global memory),
    3 = warp-per-problem (all shared memory) */

@@ -476,7 +476,41 @@ static void chol_ln(double Lm[NV][NV], int n)
 
 /* Gamma = lam/t, condensed Hessians, backward square-root Riccati factorisation
  * (HPIPM d_ocp_qp_fact_solve_kkt_step, factorisation half) */
-static void ipm_fact(const orc_config *c, ipm_mem *m)
+/* LQ factorisation with positive diagonal (BLASFEO dgelqf_pd): W (n x nc, row-major with leading dimension ld) = L Q.
+ * Householder reflections from the right, row by row; on return the lower triangle of the leading n x n block of W is L.
+ * L L^T = W W^T without ever forming the product: the condition number of the sum of squares is not squared. */
+#define LQ_MAXC (NV + 6 + ORC_MAXM + NX)
+static void lq_pd(double *W, int n, int nc, int ld)
+{
+    for (int i = 0; i < n; i++) {
+        double *wi = W + (size_t)i * ld;
+        double s2 = 0.0;
+        for (int j = i + 1; j < nc; j++) s2 += wi[j] * wi[j];
+        if (s2 > 0.0) {
+            const double x0 = wi[i];
+            const double nrmx = sqrt(x0 * x0 + s2);
+            const double alpha = x0 > 0.0 ? -nrmx : nrmx;
+            /* v = x - alpha e_i, beta = 2 / v^T v = 1 / (nrmx (nrmx + |x0|)) */
+            const double v0 = x0 - alpha;
+            const double beta = 1.0 / (nrmx * (nrmx + fabs(x0)));
+            for (int r = i + 1; r < n; r++) {
+                double *wr = W + (size_t)r * ld;
+                double d = wr[i] * v0;
+                for (int j = i + 1; j < nc; j++) d += wr[j] * wi[j];
+                d *= beta;
+                wr[i] -= d * v0;
+                for (int j = i + 1; j < nc; j++) wr[j] -= d * wi[j];
+            }
+            wi[i] = alpha;
+            for (int j = i + 1; j < nc; j++) wi[j] = 0.0;
+        }
+        if (wi[i] < 0.0) for (int r = i; r < n; r++) W[(size_t)r * ld + i] = -W[(size_t)r * ld + i];   /* positive diagonal */
+    }
+}
+
+/* use_lq: HPIPM d_ocp_qp_fact_lq_solve_kkt_step -- the node matrix is never summed up; its Cholesky factor is the L of
+ * an LQ factorisation of [chol(H + reg I) | sqrt(Gamma_b) | C^T sqrt(Gamma_g) | BAt Lxx(k+1)] */
+static void ipm_fact(const orc_config *c, ipm_mem *m, int use_lq)
 {
     const int N = m->N;
     for (int k = N; k >= 0; k--) {
@@ -488,9 +522,22 @@ static void ipm_fact(const orc_config *c, ipm_mem *m)
         double Mx[NV][NV];
         for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) Mx[i][j] = q->H[i][j];
         for (int i = 0; i < nv; i++) Mx[i][i] += c->reg_prim;
+        double Wq[NV][LQ_MAXC];
+        int ncol = 0;
+        if (use_lq) {
+            /* first block: Cholesky factor of the Hessian itself (HPIPM keeps it across iterations: use_hess_fact) */
+            double Lh[NV][NV];
+            for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) Lh[i][j] = Mx[i][j];
+            chol_ln(Lh, nv);
+            memset(Wq, 0, sizeof(Wq));
+            for (int i = 0; i < nv; i++) for (int j = 0; j <= i; j++) Wq[i][j] = Lh[i][j];
+            ncol = nv;
+        }
         for (int j = 0; j < q->nb; j++) {
             int iv = q->idxb[j];
-            Mx[iv][iv] += w->Gam[OFF_LB(q) + j] + w->Gam[OFF_UB(q) + j];
+            const double gam = w->Gam[OFF_LB(q) + j] + w->Gam[OFF_UB(q) + j];
+            Mx[iv][iv] += gam;
+            if (use_lq) { Wq[iv][ncol] = gam > 0.0 ? sqrt(gam) : 0.0; ncol++; }
         }
         for (int j = 0; j < q->ng; j++) {
             double wl = w->Gam[OFF_LG(q) + j], wu = w->Gam[OFF_UG(q) + j], weff;
@@ -502,6 +549,11 @@ static void ipm_fact(const orc_config *c, ipm_mem *m)
             } else weff = wl + wu;
             for (int a = 0; a < nv; a++) for (int b2 = 0; b2 < nv; b2++)
                 Mx[a][b2] += weff * q->Ct[a][j] * q->Ct[b2][j];
+            if (use_lq) {
+                const double sw = weff > 0.0 ? sqrt(weff) : 0.0;
+                for (int a = 0; a < nv; a++) Wq[a][ncol] = q->Ct[a][j] * sw;
+                ncol++;
+            }
         }
         if (k < N) {
             /* AL = BAt * Lxx(k+1)  (dtrmm), M += AL AL^T (dsyrk) */
@@ -518,10 +570,19 @@ static void ipm_fact(const orc_config *c, ipm_mem *m)
                 for (int r = 0; r < nxn; r++) a += AL[i][r] * AL[j][r];
                 Mx[i][j] += a;
             }
+            if (use_lq) {
+                for (int i = 0; i < nv; i++) for (int r = 0; r < nxn; r++) Wq[i][ncol + r] = AL[i][r];
+                ncol += nxn;
+            }
         }
-        for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) w->L[i][j] = Mx[i][j];
-        chol_ln(w->L, nv);
-        if (c->reserved == 1 && nu == 2 && q->nx == NX) {
+        if (use_lq) {
+            lq_pd(&Wq[0][0], nv, ncol, LQ_MAXC);
+            for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) w->L[i][j] = j <= i ? Wq[i][j] : 0.0;
+        } else {
+            for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) w->L[i][j] = Mx[i][j];
+            chol_ln(w->L, nv);
+        }
+        if (c->lq_fact == -1 && nu == 2 && q->nx == NX) {
             /* DEBUG/ANALYSIS ONLY: classical Riccati -- replace Lxx by chol(Mxx - Mxu Muu^-1 Mux) with the
              * Schur complement formed explicitly through the 2x2 inverse (what a naive GPU kernel would do) */
             double det = Mx[0][0] * Mx[1][1] - Mx[1][0] * Mx[1][0], di = 1.0 / det;
@@ -782,7 +843,7 @@ static int ipm_solve_qp(const orc_config *c, ipm_mem *m, int *iter_out, double *
     const int N = m->N;
     double mu, nrm[4], lnrm[4];
     double alpha = 1.0;
-    int n_itref = 0, n_lq = 0;
+    int n_itref = 0, n_lq = 0, force_lq = 0;
     ipm_init(c, m);
     ipm_res(m, m->res, &mu, nrm);
     int kk;
@@ -792,17 +853,30 @@ static int ipm_solve_qp(const orc_config *c, ipm_mem *m, int *iter_out, double *
         /* backup complementarity residual */
         for (int k = 0; k <= N; k++) memcpy(m->rm_bkp + (size_t)k * MAXC, m->res[k].rm, MAXC * sizeof(double));
         /* predictor (affine scaling) direction */
-        ipm_fact(c, m);
-        ipm_solve(m, m->res, m->step);
-        /* lq_fact==1: HPIPM checks the accuracy of the Cholesky solve and switches to an
-         * LQ-based factorisation when the linear residual of the predictor exceeds 1e-5 (absolute).  NOT restated:
-         * we only count the event (stats[7]).  With barrier weights of 1e15+ the absolute bar is exceeded at some
-         * iteration in ~40 % of random cold-start problems (59 % of those that run into the iteration limit); the
-         * square-root Cholesky used here + iterative refinement give the same steps up to rounding, see DESIGN.md 2 */
-        ipm_res_lin(m, m->res, m->step, m->lin, lnrm);
-        if (!(lnrm[0] <= 1e-5 && lnrm[1] <= 1e-5 && lnrm[2] <= 1e-5 && lnrm[3] <= 1e-5)) n_lq++;
+        /* HPIPM lq_fact (mode BALANCE: 1): 0 = Cholesky of the summed node matrix always; 1 = Cholesky, but the accuracy of
+         * the predictor is checked (residual of the linear system, absolute bar 1e-5 on every block, NaN counts as
+         * inaccurate) and on failure the iteration is REDONE with the LQ-based factorisation, which then stays on for
+         * the rest of the solve (force_lq); 2 = LQ always.  stats[7] counts the iterations that used LQ. */
+        if (c->lq_fact <= 0) {
+            ipm_fact(c, m, 0);
+            ipm_solve(m, m->res, m->step);
+        } else if (c->lq_fact == 1 && !force_lq) {
+            ipm_fact(c, m, 0);
+            ipm_solve(m, m->res, m->step);
+            ipm_res_lin(m, m->res, m->step, m->lin, lnrm);
+            if (!(lnrm[0] <= 1e-5 && lnrm[1] <= 1e-5 && lnrm[2] <= 1e-5 && lnrm[3] <= 1e-5)) {
+                ipm_fact(c, m, 1);
+                ipm_solve(m, m->res, m->step);
+                force_lq = 1;
+                n_lq++;
+            }
+        } else {
+            ipm_fact(c, m, 1);
+            ipm_solve(m, m->res, m->step);
+            n_lq++;
+        }
 #ifdef ORC_DEBUG
-        fprintf(stderr, "it %d mu %.3e res %.2e %.2e %.2e %.2e | lin %.2e %.2e %.2e %.2e\n", kk, mu, nrm[0], nrm[1], nrm[2], nrm[3], lnrm[0], lnrm[1], lnrm[2], lnrm[3]);
+        fprintf(stderr, "it %d mu %.3e res %.2e %.2e %.2e %.2e | lq %d\n", kk, mu, nrm[0], nrm[1], nrm[2], nrm[3], force_lq);
 #endif
         alpha = ipm_alpha(m, m->step);
         if (c->pred_corr) {

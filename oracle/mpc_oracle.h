@@ -48,7 +48,10 @@ typedef struct orc_config {
     int32_t soft;            /* robot_ocp_problem.py:106 `slack` */
     int32_t qp_iter_max;     /* QP_ITER, world_specification.py:48 */
     int32_t lm_scaled_by_dt; /* acados-version switch, SURVEY Appendix A */
-    int32_t pred_corr, cond_pred_corr, itref_corr_max, reserved;
+    int32_t pred_corr, cond_pred_corr, itref_corr_max;
+    int32_t lq_fact;         /* HPIPM lq_fact: 0 Cholesky only, 1 switch to the LQ factorisation when the predictor is
+                                inaccurate (mode BALANCE, what acados installs), 2 LQ always; -1 = analysis only: classical
+                                (non-square-root) Riccati recursion */
     double tf;               /* TF, world_specification.py:43 */
     double lm;               /* levenberg_marquardt, robot_ocp_problem.py:128 */
     double W[6];             /* diag of W over y=[x,y,v,omega,u_a,u_alpha], :78-80 */

@@ -34,7 +34,7 @@ class OrcConfig(C.Structure):
         ("N", C.c_int32), ("M", C.c_int32), ("integrator", C.c_int32), ("soft", C.c_int32),
         ("qp_iter_max", C.c_int32), ("lm_scaled_by_dt", C.c_int32),
         ("pred_corr", C.c_int32), ("cond_pred_corr", C.c_int32),
-        ("itref_corr_max", C.c_int32), ("reserved", C.c_int32),
+        ("itref_corr_max", C.c_int32), ("lq_fact", C.c_int32),
         ("tf", C.c_double), ("lm", C.c_double),
         ("W", C.c_double * 6), ("We", C.c_double * 4),
         ("lbx", C.c_double * 4), ("ubx", C.c_double * 4),

@@ -203,3 +203,182 @@ def test_closed_loop_reproduces_the_reference_runs_per_seed(torch_cuda, stamp):
     assert np.corrcoef(ref[both, 4], ours[both, 4])[0, 1] >= 0.45
     assert abs(ours[:, 4].mean() - ref[:, 4].mean()) <= 0.25 * ref[:, 4].mean()
     assert abs(ours[:, 0].mean() - ref[:, 0].mean()) <= 0.12 and abs(ours[:, 1].mean() - ref[:, 1].mean()) <= 0.12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: fused closed-loop entry (b2mpc_closed_loop), device Philox noise, re-entrant step(), RL env against the oracle
+def _philox4x32_10(c, k):
+    """numpy restatement of Philox4x32-10 (Salmon et al., SC'11) for one counter/key: the check of the device generator"""
+    c = [np.uint32(v) for v in c]; k = [np.uint32(v) for v in k]
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0 = M0 * np.uint64(c[0]); p1 = M1 * np.uint64(c[2])
+        c = [np.uint32(p1 >> np.uint64(32)) ^ c[1] ^ k[0], np.uint32(p1 & np.uint64(0xffffffff)),
+             np.uint32(p0 >> np.uint64(32)) ^ c[3] ^ k[1], np.uint32(p0 & np.uint64(0xffffffff))]
+        k = [np.uint32((int(k[0]) + 0x9E3779B9) & 0xffffffff), np.uint32((int(k[1]) + 0xBB67AE85) & 0xffffffff)]
+    return [int(v) for v in c]
+
+
+def _philox_normal2(seed, env, step, obstacle):
+    r = _philox4x32_10([step, obstacle, env & 0xffffffff, env >> 32], [seed & 0xffffffff, seed >> 32])
+    u1 = ((r[0] >> 5) * 67108864.0 + (r[1] >> 6) + 0.5) / 9007199254740992.0
+    u2 = ((r[2] >> 5) * 67108864.0 + (r[3] >> 6) + 0.5) / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    return rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
+
+
+def test_philox_known_answer():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors): zero counter/key, all-ones, and pi digits"""
+    assert _philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_device_philox_noise_stream(torch_cuda):
+    """noise_mode 1 of b2mpc_closed_loop: the obstacle velocities after each control step reveal the N(0,1) draws
+    (visualization.py:28-33: v <- clip((1 + 0.1 n) v)); they must be the Philox4x32-10 + Box-Muller stream keyed by
+    (seed, global environment index, control step, obstacle) -- for any batch composition."""
+    from b200mpc.closed_loop import BatchedRobotOcp
+    dims = world.MpcDims(20, 5, 2.0)
+    B, seed = 6, 0x1234567
+    obst = np.zeros((B, 5, 4)); obst[:, :, 0] = 3.0; obst[:, :, 1] = -3.0; obst[:, :, 2] = 1.0; obst[:, :, 3] = -1.0
+    start = np.array([-6.0, -6.0, np.pi / 4, 0.0, 0.0]); goal = np.array([6.0, 6.0])
+    ocp = BatchedRobotOcp(start, goal, obst, dims, init_guess_when_error=True, random_move=True, seed=seed)
+    ocp.set_initial_guess()
+    v_prev = obst[:, :, 2:4].copy()
+    for step in range(3):
+        ocp.advance(1)
+        v = ocp.solver.get("obst", B, host=True)[:, :, 2:4]
+        n = (v / v_prev - 1.0) / 0.1
+        for b in range(B):
+            for j in range(5):
+                n0, n1 = _philox_normal2(seed, b, step, j)
+                assert abs(n[b, j, 0] - n0) < 1e-9 and abs(n[b, j, 1] - n1) < 1e-9, (step, b, j)
+        v_prev = v.copy()
+    ocp.solver.close()
+    # environments 3..5 alone, told their global index: the same stream, the same trajectories
+    sub = BatchedRobotOcp(start, goal, obst[3:], dims, init_guess_when_error=True, random_move=True, seed=seed, env_offset=3)
+    sub.set_initial_guess(); sub.advance(3)
+    full = BatchedRobotOcp(start, goal, obst, dims, init_guess_when_error=True, random_move=True, seed=seed)
+    full.set_initial_guess(); full.advance(3)
+    assert np.array_equal(sub.solver.get("obst", 3, host=True), full.solver.get("obst", B, host=True)[3:])
+    assert np.array_equal(sub.solver.get("x0", 3, host=True), full.solver.get("x0", B, host=True)[3:])
+    sub.solver.close(); full.solver.close()
+
+
+def test_fused_closed_loop_equals_the_stepwise_loop(torch_cuda):
+    """b2mpc_closed_loop (one C call per chunk, three launches per control step, finished environments leave the queue)
+    against the loop sequenced phase by phase from Python: bit-identical states, margins, flags and step counts"""
+    from b200mpc.closed_loop import BatchedRobotOcp
+    dims = world.MpcDims(20, 5, 2.0)
+    seeds, steps = list(range(24)), 150
+    streams = [world.reference_episode_streams(s, "RANDOM", 5, steps, True) for s in seeds]
+    obst = np.stack([o for o, _ in streams]); noise = np.ascontiguousarray(np.stack([n for _, n in streams], axis=1))
+    start = np.array([-7.0, -7.0, np.pi / 4, 0.0, 0.0]); goal = np.array([7.0, 7.0])
+    res = []
+    for fused in (True, False):
+        ocp = BatchedRobotOcp(start, goal, obst, dims, init_guess_when_error=True, random_move=True, noise=noise)
+        ocp.solver.loop_begin(len(seeds)); ocp.set_initial_guess()
+        (ocp.advance if fused else ocp.advance_stepwise)(steps, check_every=16)
+        res.append(ocp.outcome() + (ocp.solver.get("x", len(seeds), host=True), ocp.solver.get("obst", len(seeds), host=True)))
+        ocp.solver.close()
+    assert res[0][2].sum() >= 8 and (~res[0][2]).sum() >= 1          # some reached the goal (left the queue), some still run
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+def test_step_is_reentrant_after_set_subgoal(torch_cuda):
+    """RobotOcpProblem.step() starts every call with reached_subgoal = False and i = 0 (robot_ocp_problem.py:177-183): after an
+    environment reached its sub-goal, set_subgoal(new) + step() must drive it on; min_margin_traj is kept (:51)"""
+    from b200mpc.closed_loop import BatchedRobotOcp
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 4
+    obst = np.zeros((B, 5, 4)); obst[:, :, 0] = 7.5; obst[:, :, 1] = -7.5          # parked in a corner, out of the way
+    start = np.array([-5.0, -5.0, np.pi / 4, 0.0, 0.0])
+    ocp = BatchedRobotOcp(start, np.array([-3.0, -3.0]), obst, dims, init_guess_when_error=True, random_move=False)
+    x1, hit1, reached1, mm1, dist1, steps1, oob1 = ocp.step(120)
+    assert reached1.all() and (steps1 > 3).all() and (dist1 <= world.TOL).all()
+    ocp.set_subgoal(np.array([0.0, -3.0]))
+    x2, hit2, reached2, mm2, dist2, steps2, oob2 = ocp.step(120)
+    assert reached2.all() and (np.abs(x2[:, 0] - 0.0) < 0.2).all()          # it moved to the NEW sub-goal
+    assert (steps2 > 3).all() and (steps2 < 120).all()                      # per-call step count, not cumulative
+    assert (mm2 <= mm1 + 1e-12).all()                                       # the episode's minimum margin is kept
+    ocp.solver.close()
+
+
+def test_set_subgoal_moves_stage_and_terminal_references(torch_cuda):
+    """robot_ocp_problem.py:279-284, fixed variant (the reference writes a 5-vector into the 4-dimensional terminal
+    reference and leaves the stage references at the old goal): yref of EVERY node and the slack-weight goal follow"""
+    from b200mpc.closed_loop import BatchedRobotOcp
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 3
+    obst = np.zeros((B, 5, 4)); obst[:, :, 0] = 7.5; obst[:, :, 1] = 7.5
+    ocp = BatchedRobotOcp(np.array([0.0, 0.0, 0.0, 0.0, 0.0]), np.array([6.0, 6.0]), obst, dims)
+    sub = np.array([[1.0, 2.0], [-3.0, 4.0], [5.0, -6.0]])
+    ocp.set_subgoal(sub)
+    yref = ocp.solver.get("yref", B, host=True)
+    assert yref.shape == (B, 21, 6)
+    assert np.array_equal(yref[:, :, 0:2], np.repeat(sub[:, None, :], 21, axis=1)) and (yref[:, :, 2:] == 0).all()
+    assert np.array_equal(ocp.solver.get("goal", B, host=True), sub)
+    ocp.solver.prepare_slack(B)
+    zl = ocp.solver.get("zl", B, host=True)
+    exp = 1e4 * ((sub ** 2).sum(1) + 50.0)                                  # x0 = 0: alpha_0 = 1e4 (|x0 - subgoal|^2 + 50)
+    assert np.allclose(zl[:, 0, 0], exp, rtol=1e-15)
+    ocp.solver.close()
+
+
+def test_rl_env_step_tracks_the_oracle_loop(torch_cuda, oracle):
+    """BatchedMpcEnv.step(action) = set_subgoal(action) + mpc_steps control steps of robot_ocp_problem.py:184-260: the robot
+    states it returns are those of the oracle-driven loop with the same sub-goal (compared while the QPs converge)"""
+    from b200mpc.rl_env import BatchedMpcEnv
+    B, mpc_steps = 8, 5
+    env = BatchedMpcEnv(B, mpc_steps=mpc_steps, max_env_steps=30, seed=11, random_move=False)
+    state = env.reset()
+    _, x0, obst0 = env._observe()
+    action = np.stack([np.linspace(-2, 3, B), np.linspace(1, -4, B)], axis=1)
+    cfg = oracle.default_config(20, 5, 2.0)
+    checked = 0
+    state1, reward, done, info = env.step(action)
+    it_gpu = env.ocp.solver.get_int("qp_iter", B, host=True)
+    for b in range(B):
+        log = _oracle_episode(oracle, cfg, obst0[b], np.zeros((mpc_steps, 5, 2)), x0[b], action[b], mpc_steps)
+        if any(entry[2] >= 50 for entry in log) or it_gpu[b] >= 50:
+            continue                                   # a QP cut off by the iteration limit: the two loops may separate
+        checked += 1
+        assert np.abs(state1[b, :2] - log[-1][0][:2]).max() < 1e-5, b
+        assert abs(info["min_margin"][b] - log[-1][3]) < 1e-5
+    assert checked >= 3
+    env.close()
+
+
+def test_two_gpus_give_bit_identical_shards(torch_cuda):
+    """per-problem results do not depend on the number of shards -- one handle on device 0 solving all scenarios
+    against two handles (devices 0 and 1, used from ONE thread: every entry point switches to its handle's device) solving
+    half each.  Skipped on a single-GPU box."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from b200mpc import BatchedMpcSolver, sharding
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 512
+    sc = world.random_scenarios(B, dims, seed=13, moving_start=True)
+    names = ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")
+
+    def run(device, lo, hi):
+        s = BatchedMpcSolver(20, 5, 2.0, max_batch=hi - lo, device=device, kernel=2)
+        with torch.cuda.device(device):
+            for nme in names:
+                s.set(nme, torch.from_numpy(np.ascontiguousarray(sc[nme][lo:hi])).to(f"cuda:{device}"))
+            s.solve(hi - lo)
+            out = (s.get("x", hi - lo).cpu().numpy(), s.get("u", hi - lo).cpu().numpy(), s.get_int("qp_iter", hi - lo).cpu().numpy())
+        return s, out
+    s_all, full = run(0, 0, B)
+    (lo0, hi0), (lo1, hi1) = [sharding.shard_bounds(B, r, 2) for r in (0, 1)]
+    sa, a = run(0, lo0, hi0)
+    sb, b = run(1, lo1, hi1)                                 # created while device 0's handles are alive
+    sa.solve(hi0 - lo0)                                      # ... and device 0 still works afterwards, from the same thread
+    for k in range(3):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), full[k])
+    for s in (s_all, sa, sb):
+        s.close()
