@@ -806,6 +806,7 @@ struct B2LoopArgs {
     int32_t *STEPS, *DONE, *OOB, *NFAIL;
     B2Noise nz;
     int random_move, init_guess_when_error, quirk, do_post, do_pre;
+    int key_mode;             // 0: previous iteration count where available, 1: always the geometric predictor (experiment: B2MPC_LOOP_KEY=geo)
     double tol;
     int32_t *key, *hist;
 };
@@ -825,7 +826,7 @@ __global__ void b2_loop_glue(B2Params p, B2LoopArgs a)
     b2_slack_one(a.X0w, a.GOAL, const_cast<double*>(p.ZL), const_cast<double*>(p.ZZL), p.N, p.M, b, p.Bm);
     const int it = p.QP_ITER[b];
     int kk;
-    if (!fresh && it > 0) kk = B2_ORDER_NODEKEYS - 1 - (it < B2_ORDER_NODEKEYS ? it : B2_ORDER_NODEKEYS - 1);
+    if (!fresh && it > 0 && a.key_mode == 0) kk = B2_ORDER_NODEKEYS - 1 - (it < B2_ORDER_NODEKEYS ? it : B2_ORDER_NODEKEYS - 1);
     else kk = b2_order_key_one(p.X, p.P, p.N, p.M, p.r2, b, p.Bm);
     a.key[b] = kk;
     atomicAdd(&a.hist[kk], 1);
@@ -911,7 +912,6 @@ extern "C" int b2mpc_closed_loop(b2mpc* h, int64_t batch, int32_t steps, int32_t
     if (steps < 0) return fail(B2MPC_EINVAL, "steps must be >= 0");
     if (noise_mode < 0 || noise_mode > 2) return fail(B2MPC_EINVAL, "noise_mode must be 0 (none), 1 (device Philox stream) or 2 (replay)");
     if (noise_mode == 2 && !dnoise) return fail(B2MPC_EINVAL, "noise_mode 2 needs a device noise stream [steps][batch][M][2]");
-    if (h->cfg.nlp_solver == 1) return fail(B2MPC_EINVAL, "the closed loop is the reference's SQP_RTI loop (cfg.nlp_solver = 0)");
     if (steps == 0) return B2MPC_OK;
     B2DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -924,6 +924,7 @@ extern "C" int b2mpc_closed_loop(b2mpc* h, int64_t batch, int32_t steps, int32_t
     a.STEPS = h->fi[B2MPC_STEPS]; a.DONE = h->fi[B2MPC_DONE]; a.OOB = h->fi[B2MPC_OOB]; a.NFAIL = h->fi[B2MPC_NFAIL];
     a.random_move = random_move; a.init_guess_when_error = init_guess_when_error; a.quirk = quirk_vx_is_vy; a.tol = tol;
     a.key = o.key;
+    { const char* e = getenv("B2MPC_LOOP_KEY"); a.key_mode = (e && e[0] == 'g') ? 1 : 0; }
     const unsigned ob = (unsigned)((batch + 127) / 128);
     const size_t noise_stride = (size_t)batch * h->M * 2;
     int cur = 0;
@@ -937,7 +938,7 @@ extern "C" int b2mpc_closed_loop(b2mpc* h, int64_t batch, int32_t steps, int32_t
                                              o.hist[cur ^ 1], o.fill[cur ^ 1]);
         h->launches++;
         p.ORDER = o.order; p.NEXT = o.next; p.NQ = o.nq;
-        if ((rc = launch_solve(h, p, batch, false, st))) return rc;
+        if ((rc = launch_solve(h, p, batch, h->cfg.nlp_solver == 1, st))) return rc;      // (nlp_solver = 1: a full SQP solve per control step)
         cur ^= 1;
         a.do_post = 1; a.do_pre = (i + 1 < steps) ? 1 : 0; a.hist = o.hist[cur];
         a.nz = B2Noise{random_move ? noise_mode : 0, noise_mode == 2 ? dnoise + (size_t)i * noise_stride : nullptr, seed, env_offset,
