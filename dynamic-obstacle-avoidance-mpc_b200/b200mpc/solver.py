@@ -199,7 +199,7 @@ class BatchedMpcSolver:
 
     @property
     def kernel_name(self):
-        return {2: "warp-per-problem", 3: "warp-per-problem (all shared)"}[self.kernel_id]
+        return {2: "warp-per-problem", 3: "warp-per-problem (all shared)", 4: "cta-per-problem"}[self.kernel_id]
 
     @property
     def launch_count(self):

@@ -14,6 +14,7 @@
 #include "mpc_common.cuh"
 #include "mpc_params.h"
 #include "mpc_wpp.cuh"
+#include "mpc_cta.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...)
@@ -66,6 +67,9 @@ struct b2mpc {
     size_t wpp_smem_sqp, wpriv_stride_sqp;
     size_t wpp_smem_small;
     int small_batch_max;
+    void (*cta_fn)(const B2Params);         // CTA-per-problem latency kernel (mpc_cta.cuh), reference dimensions only
+    size_t cta_smem;
+    int cta_threads, cta_grid;
     B2Params prm;
 };
 
@@ -169,6 +173,14 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
     const bool ref_dims = (M == 5 && N == 20);          // the reference's configuration (world_specification.py:44-48)
     const bool ref_dims_short = (M == 5 && N == 10);    // the reference's other recorded setting: TF = 1 s => N_SOLV = 10
     const bool long_dims = (M == 20 && N == 100);       // BASELINE.json config 4
+    if (cfg->kernel < 0 || cfg->kernel > 4) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "kernel must be 0 (auto), 2, 3 or 4"); }
+    if (ref_dims) { h->cta_fn = b2_rti_solve_cta<5, 20>; h->cta_threads = CtaSolver<5, 20>::NTHR; }
+    else if (ref_dims_short) { h->cta_fn = b2_rti_solve_cta<5, 10>; h->cta_threads = CtaSolver<5, 10>::NTHR; }
+    if (cfg->kernel == 4 && !h->cta_fn) {
+        b2mpc_destroy(h);
+        return fail(B2MPC_EINVAL, "kernel 4 (CTA-per-problem) is instantiated for the reference's dimensions: 5 obstacles, N = 20 or N = 10");
+    }
+    if (cfg->kernel == 4 && cfg->nlp_solver == 1) { b2mpc_destroy(h); return fail(B2MPC_EINVAL, "kernel 4 runs SQP_RTI only (nlp_solver = 0)"); }
     if (cfg->kernel == 3) {
         smask = smask_sqp = B2_WPP_ALL_SHARED;
         if (b2_wpp_smem_bytes(N, M, smask) > (size_t)max_smem) {
@@ -184,7 +196,21 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
                   : long_dims ? b2_rti_solve_wpp<20, 100, B2_WPP_LONG> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL>;
         if (long_dims) smask = B2_WPP_LONG;                  // v, pi, dv, dpi, cpi, pv in global memory too: 4 CTAs/SM instead of 2
         h->wpp_fn_sqp = ref_dims ? b2_rti_solve_wpp<5, 20, B2_WPP_ALL_GLOBAL, true> : b2_rti_solve_wpp<0, 0, B2_WPP_ALL_GLOBAL, true>;
-        h->kernel = 2;
+        h->kernel = cfg->kernel == 4 ? 4 : 2;
+    }
+    if (h->cta_fn) {
+        h->cta_smem = b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED);
+        int occ_c = 0, sms_c = 0;
+        cudaDeviceGetAttribute(&sms_c, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (h->cta_smem > (size_t)max_smem ||
+            cudaFuncSetAttribute(h->cta_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cta_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(h->cta_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, h->cta_fn, h->cta_threads, h->cta_smem) != cudaSuccess || occ_c < 1) {
+            if (cfg->kernel == 4) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "CTA-per-problem kernel does not fit an SM"); }
+            h->cta_fn = nullptr;
+        }
+        h->cta_grid = occ_c * sms_c;
+        if (const char* e = getenv("B2MPC_CTA_GRID")) { if (atoi(e) > 0) h->cta_grid = atoi(e); }       // experiment: resident CTAs
     }
     {
         h->wpp_smem = b2_wpp_smem_bytes(N, M, smask);
@@ -852,6 +878,9 @@ static int launch_solve(b2mpc* h, B2Params& p, int64_t batch, bool sqp, cudaStre
         const unsigned blocks = (unsigned)(batch < h->wpp_grid ? batch : h->wpp_grid);
         p.wpriv_stride = h->wpriv_stride_sqp;
         h->wpp_fn_sqp<<<blocks, 32, h->wpp_smem_sqp, st>>>(p);
+    } else if (h->kernel == 4) {
+        const unsigned blocks = (unsigned)(batch < h->cta_grid ? batch : h->cta_grid);      // persistent: one CTA per resident slot
+        h->cta_fn<<<blocks, h->cta_threads, h->cta_smem, st>>>(p);
     } else if (h->wpp_fn_small && batch <= h->small_batch_max) {
         h->wpp_fn_small<<<(unsigned)batch, 32, h->wpp_smem_small, st>>>(p);            // one wave, everything on chip
     } else {

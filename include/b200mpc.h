@@ -52,7 +52,9 @@ typedef struct b2mpc_config {
     int32_t lm_scaled_by_dt; /* acados-version switch for levenberg_marquardt scaling */
     int32_t kernel;          /* 0 = auto (2; batches that fit the GPU in one wave: 3), 2 = warp-per-problem with the node-private
                                 rows in L2-resident global memory (any N <= 128), 3 = warp-per-problem, everything in shared
-                                memory (needs the whole problem to fit: N = 20, M = 5 does).  1 (a thread-per-problem
+                                memory (needs the whole problem to fit: N = 20, M = 5 does), 4 = CTA-per-problem (mpc_cta.cuh:
+                                five warps per problem, everything in shared memory, the latency-oriented mapping; reference
+                                dimensions only: 5 obstacles, N = 20 or 10; SQP_RTI only).  1 (a thread-per-problem
                                 cross-check kernel) was removed in ABI 3: EINVAL */
     int32_t pred_corr, cond_pred_corr, itref_corr_max, reserved;
     double tf;               /* solver_options.tf, :132 */
@@ -191,7 +193,7 @@ int b2mpc_closed_loop(b2mpc *h, int64_t batch, int32_t steps, int32_t noise_mode
                       int32_t quirk_vx_is_vy, double tol, void *stream);
 
 /* which solve kernel the handle resolved to: 2 = warp-per-problem (node-private rows in global memory),
-   3 = warp-per-problem (all shared memory) */
+   3 = warp-per-problem (all shared memory), 4 = CTA-per-problem */
 int b2mpc_kernel(const b2mpc *h);
 /* number of kernels launched by this handle so far (for bench accounting) */
 int64_t b2mpc_launch_count(const b2mpc *h);

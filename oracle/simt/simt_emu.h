@@ -38,6 +38,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __constant__ static const
+#define __shared__ static thread_local          /* static shared variables: one block at a time per host thread */
 #define __launch_bounds__(...)
 #define __maxnreg__(...)
 

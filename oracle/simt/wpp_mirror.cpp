@@ -20,6 +20,7 @@
 
 #include "../../dynamic-obstacle-avoidance-mpc_b200/csrc/mpc_params.h"
 #include "../../dynamic-obstacle-avoidance-mpc_b200/csrc/mpc_wpp.cuh"
+#include "../../dynamic-obstacle-avoidance-mpc_b200/csrc/mpc_cta.cuh"
 
 namespace {
 
@@ -48,7 +49,8 @@ extern "C" {
  *   x[B,(N+1)*5] u[B,N*2] sl,su[B,(N+1)*M]                   iterate, in/out
  *   pi[B,N*5] lam,t[B,(N+1)*(12+4M)] stats[B,8]              outputs (pi/lam/t are in/out in SQP mode; may be NULL otherwise)
  *   status, qp_iter, qp_status, sqp_iter [B]                 outputs (sqp_iter may be NULL)
- * layout: 2 = node-private rows in "global" memory (the persistent throughput kernel), 3 = everything in shared memory.
+ * layout: 2 = node-private rows in "global" memory (the persistent throughput kernel), 3 = everything in shared memory,
+ *         4 = the CTA-per-problem latency kernel (mpc_cta.cuh; M = 5, N = 20 or 10, RTI only).
  * sqp: 0 = one RTI iteration (cfg->nlp_solver ignored), 1 = the full SQP loop.
  * Returns 0, or -1 for an unsupported configuration. */
 int b2mirror_solve(const b2mpc_config* cfg, int layout, int sqp, int64_t B, int host_threads,
@@ -58,7 +60,8 @@ int b2mirror_solve(const b2mpc_config* cfg, int layout, int sqp, int64_t B, int 
 {
     const int N = cfg->N, M = cfg->n_obst, nct = 12 + 4 * M;
     if (N < 1 || N > B2MPC_MAX_N || M < 1 || M > B2MPC_MAX_OBST || B < 1) return -1;
-    if (layout != 2 && layout != 3) return -1;
+    if (layout != 2 && layout != 3 && layout != 4) return -1;
+    if (layout == 4 && (sqp || M != 5 || (N != 20 && N != 10))) return -1;      // CTA-per-problem kernel: reference dimensions, RTI
     B2Params prm;
     b2_params_from_config(*cfg, (int)B, prm);
     prm.B = (int)B;
@@ -89,7 +92,12 @@ int b2mirror_solve(const b2mpc_config* cfg, int layout, int sqp, int64_t B, int 
     if (host_threads < 1) host_threads = 1;
 #define RUN(MT, NT, SM) do { if (sqp) run_kernel<MT, NT, SM, true>(prm, grid, smem, host_threads); \
                              else run_kernel<MT, NT, SM, false>(prm, grid, smem, host_threads); } while (0)
-    if (layout == 3) { if (ref_dims) RUN(5, 20, B2_WPP_ALL_SHARED); else RUN(0, 0, B2_WPP_ALL_SHARED); }
+    if (layout == 4) {
+        const size_t smem4 = b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED);
+        if (N == 20) simt::run_grid(grid, CtaSolver<5, 20>::NTHR, smem4, host_threads, [&]() { b2_rti_solve_cta<5, 20>(prm); });
+        else simt::run_grid(grid, CtaSolver<5, 10>::NTHR, smem4, host_threads, [&]() { b2_rti_solve_cta<5, 10>(prm); });
+    }
+    else if (layout == 3) { if (ref_dims) RUN(5, 20, B2_WPP_ALL_SHARED); else RUN(0, 0, B2_WPP_ALL_SHARED); }
     else if (ref_dims) RUN(5, 20, B2_WPP_ALL_GLOBAL);
     else if (ref_short && !sqp) RUN(5, 10, B2_WPP_ALL_GLOBAL);
     else if (long_dims && !sqp) RUN(20, 100, B2_WPP_LONG);

@@ -9,9 +9,10 @@ if os.environ.get('B2MPC_LIB'):
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 7
-dims = world.MpcDims(20, 5, 2.0)
+NN = int(os.environ.get("B2_N", "20"))
+dims = world.MpcDims(NN, 5, NN / 10.0)
 sc = world.random_scenarios(B, dims, seed=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
-solver = BatchedMpcSolver(20, 5, 2.0, max_batch=B, kernel=kern)
+solver = BatchedMpcSolver(NN, 5, NN / 10.0, max_batch=B, kernel=kern)
 t = {k: torch.from_numpy(sc[k]).cuda() for k in ("x0", "p", "yref", "zl", "Zl", "x", "u", "sl", "su")}
 for name in ("x0", "p", "yref", "zl", "Zl"):
     solver.set(name, t[name])

@@ -66,8 +66,9 @@ def mirror():
 def _solve_gpu(torch, dims, sc, B, **cfg_over):
     if torch is None:
         from oracle import pymirror
-        out = _solve_mirror(pymirror, dims, sc, 3 if cfg_over.get("kernel") == 3 else 2, **cfg_over)
-        out["kernel"] = 3 if cfg_over.get("kernel") == 3 else 2
+        lay = cfg_over.get("kernel") if cfg_over.get("kernel") in (3, 4) else 2
+        out = _solve_mirror(pymirror, dims, sc, lay, **cfg_over)
+        out["kernel"] = lay
         return out
     from b200mpc import BatchedMpcSolver
     solver = BatchedMpcSolver(dims.N, dims.M, dims.tf, max_batch=B, device=0, **cfg_over)
@@ -212,6 +213,23 @@ def test_rti_solve_matches_mirror_and_oracle(torch_cuda, oracle, mirror, N, M, t
     # exit residuals below the HPIPM tolerances for converged problems (KKT residual bar)
     assert (out["stats"][conv, 0] <= 1e-6).all() and (out["stats"][conv, 1] <= 1e-8).all()
     assert (out["stats"][conv, 2] <= 1e-8).all() and (out["stats"][conv, 3] <= 1e-8).all()
+
+
+@pytest.mark.parametrize("N,tf,B", [(20, 2.0, 512), (10, 1.0, 256)])
+def test_cta_per_problem_kernel_matches_mirror_and_oracle(torch_cuda, oracle, mirror, N, tf, B):
+    """kernel 4 (mpc_cta.cuh: five warps per problem, passes parallel over (node, constraint chunk), everything in shared
+    memory): bit-identical to ITS mirror (the same source under the emulator, 160-thread blocks), the independent oracle's
+    bar, and agreement with the warp-per-problem kernel to rounding (different summation order)"""
+    dims = world.MpcDims(N, 5, tf)
+    sc = world.random_scenarios(B, dims, seed=5, moving_start=True)
+    out, ref = _solve_both(torch_cuda, oracle, dims, sc, B, kernel=4)
+    assert out["kernel"] == 4
+    _check_bit_identical(out, _solve_mirror(mirror, dims, sc, 4))
+    conv = _check_independent(out, ref)
+    assert conv.mean() > 0.3
+    wpp = _solve_gpu(torch_cuda, dims, sc, B, kernel=2)
+    assert np.mean(wpp["qp_iter"] == out["qp_iter"]) >= 0.99
+    assert _rel_rows(out["u"], wpp["u"])[conv].max() < REL_TOL
 
 
 def test_active_set_matches_oracle(torch_cuda, oracle):
