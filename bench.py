@@ -312,9 +312,12 @@ def main():
     cl_ms, cl_it = closed_loop_rate(solver, B, 40, sc)
 
     # ---------------- p50 latency of ONE problem (the reference's one-at-a-time use) ----------------
-    lat1 = None
+    lat1, lat_kernel_name = None, None
     if rank == 0:
-        s1 = BatchedMpcSolver(a.N, a.n_obst, a.tf, max_batch=1, device=local_rank, kernel=a.kernel)
+        # one problem at a time is the latency kernel's job (CTA-per-problem, mpc_cta.cuh) where it is instantiated
+        from b200mpc import latency_kernel
+        s1 = BatchedMpcSolver(a.N, a.n_obst, a.tf, max_batch=1, device=local_rank, kernel=a.kernel or latency_kernel(a.N, a.n_obst))
+        lat_kernel_name = s1.kernel_name
         one = {k: dev_t[k][:1].contiguous() for k in names_in + names_it}
         for k in names_in:
             s1.set(k, one[k])
@@ -433,6 +436,7 @@ def main():
             "config": config_dict(a, world_size),
             "kernel_resolved": kernel_name,
             "p50_latency_ms_per_batch": float(np.median(step_ms)), "p50_latency_ms_single_problem": lat1,
+            "single_problem_kernel": lat_kernel_name,
             "mean_qp_iter": mean_it, "qp_failures": int(tot_fail),
             "steady_state": {"value": tot_B * a.steps / (maxs["warm_ms"] * 1e-3), "unit": UNIT, "ms_per_step": maxs["warm_ms"] / a.steps,
                              "mean_qp_iter": sums["warm_it"] / tot_B,

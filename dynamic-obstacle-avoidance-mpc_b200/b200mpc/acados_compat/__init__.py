@@ -192,8 +192,9 @@ class AcadosOcpSolver:
 
     def solve(self):
         if self._solver is None:
-            from ..solver import BatchedMpcSolver
+            from ..solver import BatchedMpcSolver, latency_kernel
             cfg = dict(self._cfg); N = cfg.pop("N"); M = cfg.pop("n_obst"); tf = cfg.pop("tf")
+            cfg.setdefault("kernel", latency_kernel(N, M, cfg.get("nlp_solver", 0)))      # one problem at a time: the latency kernel
             self._solver = BatchedMpcSolver(N, M, tf, max_batch=1, device=self._device, **cfg)
         f = self._f
         t0 = time.perf_counter()

@@ -210,6 +210,13 @@ class BatchedMpcSolver:
         return capi.lib().b2mpc_workspace_bytes(self._h)
 
 
+def latency_kernel(N, n_obst, nlp_solver=0):
+    """`kernel` value for ONE problem at a time (the reference's own use: a single closed-loop episode): the CTA-per-problem
+    kernel where it is instantiated (5 obstacles, N = 20 or 10, SQP_RTI), else 0 (auto).  Batched throughput runs keep the
+    default: its results do not depend on the batch size or on the sharding, bit for bit."""
+    return 4 if (n_obst == 5 and N in (20, 10) and nlp_solver == 0) else 0
+
+
 def dfma_peak_tflops(device=0):
     out = C.c_double(0.0)
     capi.check(capi.lib().b2mpc_dfma_peak(device, C.byref(out)))

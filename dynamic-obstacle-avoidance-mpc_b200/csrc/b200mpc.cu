@@ -199,7 +199,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         h->kernel = cfg->kernel == 4 ? 4 : 2;
     }
     if (h->cta_fn) {
-        h->cta_smem = b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED);
+        h->cta_smem = b2_cta_smem_bytes(N, M);
         int occ_c = 0, sms_c = 0;
         cudaDeviceGetAttribute(&sms_c, cudaDevAttrMultiProcessorCount, cfg->device);
         if (h->cta_smem > (size_t)max_smem ||

@@ -3,17 +3,20 @@
 //
 // mpc_wpp.cuh gives a problem ONE warp: the node-parallel passes of an interior-point iteration (KKT residuals, barrier /
 // slack elimination, expansion of the steps, step length) then walk the 6 box slots and M obstacles of a node sequentially,
-// and the lanes beyond N+1 idle.  Here a problem owns a CTA of ceil((N+1)/NPW) warps (5 at N = 20, M = 5) and EVERYTHING of
-// the problem lives in shared memory (57 KB: four problems per SM, no scratch in global memory at all):
-//   * passes: one thread per (node, chunk), chunk 0 = the node-level algebra + the six box slots, chunk 1..M = one obstacle
-//     (its two general constraints and two slack bounds).  The M+1 chunks of a node sit in adjacent lanes; what they
-//     contribute to the node's condensed Hessian / gradient / residual is summed by a fixed shuffle tree, problem-wide
-//     reductions (mu, step length, norms) go warp butterfly -> shared memory -> every thread, in a fixed order;
-//   * sequential Riccati sweeps: warp 0 runs the factorisation and the vector sweeps of mpc_wpp.cuh unchanged (lane = matrix
-//     entry / vector component) while the other warps wait at the block barrier.
+// and the lanes beyond N+1 idle.  Here a problem owns a CTA and EVERYTHING of the problem lives in shared memory (57 KB: four
+// problems per SM, no scratch in global memory at all):
+//   * obstacle warps (4 at N = 20, M = 5): one thread per (node, obstacle) -- its two general constraints and two slack
+//     bounds; the M obstacles of a node sit in adjacent lanes and their contributions to the node's condensed Hessian /
+//     gradient / residual are summed by a fixed shuffle tree, then handed to the node warp through shared memory;
+//   * node warp (the last one): one thread per node -- the node-level algebra and the six box slots -- and the sequential
+//     Riccati sweeps of mpc_wpp.cuh (lane = matrix entry / vector component) while the obstacle warps wait at the barrier;
+//   * problem-wide reductions (mu, step length, norms): warp butterfly -> shared memory -> every thread, in a fixed order.
+// Every warp has ONE role: a first version that mixed node-level and obstacle lanes in the same warp left the warps
+// permanently split into two convergence groups (measured: 5 active lanes inside the sweeps, every shuffle through the
+// WARPSYNC.COLLECTIVE slow path, 3.4x slower than the one-warp kernel).
 // Per-problem latency is what this buys (single episodes, small batches: BASELINE config 1 and the p50 single-problem
 // latency); instantiated for the reference's dimensions (M = 5; N = 20 and N = 10).  Arithmetic is written with explicit fma()
-// like mpc_wpp.cuh; the order of the sums differs from the warp kernel (tree over chunks instead of a sequential loop), so
+// like mpc_wpp.cuh; the order of the sums differs from the warp kernel (tree over obstacles instead of a sequential loop), so
 // the two kernels agree to rounding, not bit for bit -- each has its own bit-exact CPU mirror (oracle/simt/).
 #pragma once
 #include "mpc_wpp.cuh"
@@ -22,37 +25,50 @@ template <int MT, int NT>
 struct CtaSolver {
     static constexpr unsigned long long SMASK = B2_WPP_ALL_SHARED;
     static constexpr int M = MT, N = NT, NS = (NT + 1) | 1, nct = 12 + 4 * MT;
-    static constexpr int CH = MT + 1;                       // chunks per node
-    static constexpr int NPW = 32 / CH;                     // nodes per warp in the passes
-    static constexpr int NWARPS = (NT + 1 + NPW - 1) / NPW;
+    static constexpr int NPW = 32 / MT;                     // nodes per obstacle warp
+    static constexpr int NOW = (NT + 1 + NPW - 1) / NPW;    // obstacle warps
+    static constexpr int NODE_WARP = NOW;                   // the node warp (also runs the sequential sweeps)
+    static constexpr int NWARPS = NOW + 1;
     static constexpr int NTHR = 32 * NWARPS;
-    static_assert(MT >= 1 && MT <= 7 && NWARPS <= 8, "CTA kernel: M <= 7, (N+1) <= 8 * (32 / (M+1))");
+    static_assert(MT >= 1 && MT <= 8 && NT + 1 <= 32 && NWARPS <= 8, "CTA kernel: M <= 8, N <= 31");
+    static constexpr int PHI_ROWS = 25;                     // Phi_k of the feedback form, appended to the all-shared layout
     static constexpr int o_lb = 0, o_lg = 6, o_ub = 6 + MT, o_ug = 12 + MT, o_ls = 12 + 2 * MT, o_us = 12 + 3 * MT;
 
     const B2Params& p;
     const int b, tid, lane, warp;
     double* const sm;
     const WOff o;
+    const int PHI;          // first of the 25 rows of Phi
     const size_t Bm;
-    const int c;            // chunk of this thread: 0 = node level + box slots, 1..M = obstacle c-1
-    const int lead;         // lane of chunk 0 of the same node
-    const bool act;         // the thread owns a (node, chunk) pair
+    const int c;            // obstacle warps: 1 + obstacle index of this thread; node warp: 0
+    const bool act;         // the thread owns a node (node warp) or a (node, obstacle) pair (obstacle warps)
     const int k;            // its node (clamped into range for idle threads)
     int nc;
     double mu, nrm[4], sum_lt, alpha, S1, S2;
     double rm_cdd, rm_smu;
     double ad_n, ad_d, ap_n, ap_d;
+#ifdef B2_DEBUG_CLOCK
+    long long clk_fact = 0, clk_sweep = 0, clk_all = 0, clk_head = 0, clk_prep = 0, clk_rs = 0, clk_exp = 0, clk_lin = 0;
+#endif
 
     __device__ CtaSolver(const B2Params& p_, int b_, double* sm_)
-        : p(p_), b(b_), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), sm(sm_), o(MT, SMASK, false),
-          Bm((size_t)p_.Bm), c((threadIdx.x & 31) % CH), lead((threadIdx.x & 31) - (threadIdx.x & 31) % CH),
-          act((threadIdx.x & 31) < NPW * CH && (int)(threadIdx.x >> 5) * NPW + (int)(threadIdx.x & 31) / CH <= NT),
-          k(((int)(threadIdx.x >> 5) * NPW + (int)(threadIdx.x & 31) / CH) <= NT ? ((int)(threadIdx.x >> 5) * NPW + (int)(threadIdx.x & 31) / CH) : NT)
+        : p(p_), b(b_), tid(threadIdx.x), lane(threadIdx.x & 31),
+          // the warp index through a shuffle: tells the compiler that it is WARP-UNIFORM, so that `if (warp == 0)` around the
+          // sweeps is a uniform branch and the shuffles inside are compiled for a converged warp (without it every shuffle
+          // of the factorisation went through the divergent-warp path: WARPSYNC.COLLECTIVE per SHFL, 7x slower sweeps)
+          warp(__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0)), sm(sm_), o(MT, SMASK, false),
+          PHI(WOff(MT, SMASK, false).total), Bm((size_t)p_.Bm), c((int)(threadIdx.x >> 5) == NODE_WARP ? 0 : 1 + (int)(threadIdx.x & 31) % MT),
+          act(node_of(threadIdx.x) <= NT && ((int)(threadIdx.x >> 5) == NODE_WARP || (int)(threadIdx.x & 31) < NPW * MT)),
+          k(node_of(threadIdx.x) <= NT ? node_of(threadIdx.x) : NT)
     {
         nc = 0;
         for (int kk = 0; kk <= N; kk++) nc += 2 * ((kk < N ? 2 : 0) + ((kk > 0 && kk < N) ? 4 : 0)) + 4 * M;
     }
 
+    __device__ __forceinline__ static int node_of(unsigned t)
+    {
+        return (int)(t >> 5) == NODE_WARP ? (int)(t & 31) : (int)(t >> 5) * NPW + (int)(t & 31) / MT;
+    }
     __device__ __forceinline__ double& S(int row, int kk) const { return sm[row * NS + kk]; }
     template <int F>
     __device__ __forceinline__ double& Q(int i) const { return sm[(o.pf[F] + i) * NS + k]; }
@@ -67,24 +83,28 @@ struct CtaSolver {
         const double xv = Q<PF_XU>(s);
         lb = p.lb6[s] - xv; ub = p.ub6[s] - xv;
     }
-    __device__ __forceinline__ bool is_lead() const { return act && c == 0; }
-    __device__ __forceinline__ bool is_obst() const { return act && c > 0; }
+    __device__ __forceinline__ bool node_warp() const { return warp == NODE_WARP; }       // warp-uniform
+    __device__ __forceinline__ bool is_lead() const { return act; }                        // (inside node_warp() branches)
+    __device__ __forceinline__ bool is_obst() const { return act; }                        // (inside !node_warp() branches)
+    // what the obstacles of a node add to its condensed quantities travels through dead rows of shared memory: the
+    // refinement correction cpi (5 rows) and the cost-to-go gradient pv (5 rows) are not live during the passes that use them
+    __device__ __forceinline__ double& XCH(int i) const { return i < 5 ? sm[(o.pf[PF_CPI] + i) * NS + k] : sm[(o.pf[PF_PV] + i - 5) * NS + k]; }
 
     // ---- reductions ------------------------------------------------------------------------------------------------
-    // sum over the CH adjacent lanes of a node, result in its chunk-0 lane: a fixed tree over power-of-two offsets
-    // (CH = 6: (v0 + v4 + v2) + (v1 + v5 + v3)); every lane of the warp takes part in the shuffles
+    // sum over the M adjacent lanes of a node (obstacle warps), result in the lane of obstacle 0: a fixed tree over
+    // power-of-two offsets (M = 5: (v0 + v4 + v2) + (v1 + v3)); every lane of the warp takes part in the shuffles
     __device__ __forceinline__ double seg_sum(double v) const
     {
+        const int j = c - 1;
 #pragma unroll
         for (int off = 4; off >= 1; off >>= 1) {
-            if (off < CH) {
+            if (off < MT) {
                 const double t = __shfl_down_sync(0xffffffffu, v, off);
-                if (c < off && c + off < CH) v += t;
+                if (j < off && j + off < MT) v += t;
             }
         }
         return v;
     }
-    __device__ __forceinline__ double from_lead(double v) const { return __shfl_sync(0xffffffffu, v, lead); }
 
     // problem-wide reduction of up to 8 values per thread: sums (first nsum entries) by warp butterflies, maxima of
     // non-negative values (the rest) by REDUX; the per-warp results meet in shared memory (the AL scratch of the
@@ -94,7 +114,7 @@ struct CtaSolver {
     __device__ __forceinline__ void cta_reduce(double* v)
     {
         constexpr int NV = NSUM + NMAX + NNEG;
-        double* const red = sm + o.total * NS;              // B2_WPP_SCRATCH = 40 doubles >= NWARPS * NV
+        double* const red = sm + (o.total + PHI_ROWS) * NS; // B2_WPP_SCRATCH = 40 doubles >= NWARPS * NV
         static_assert(NWARPS * NV <= B2_WPP_SCRATCH, "reduction scratch");
 #pragma unroll
         for (int i = 0; i < NSUM; i++) v[i] = b2_warp_sum(v[i]);
@@ -129,8 +149,8 @@ struct CtaSolver {
         for (int e = tid; e < 7 * NS; e += NTHR) sm[o.pf[PF_DV] * NS + e] = 0.0;
         for (int e = tid; e < 5 * NS; e += NTHR) sm[o.pf[PF_DPI] * NS + e] = 0.0;
         __syncthreads();
-        double xk[5] = {0, 0, 0, 0, 0}, v[7] = {0, 0, 0, 0, 0, 0, 0};
-        if (is_lead()) {
+        if (node_warp() && is_lead()) {
+            double xk[5], v[7] = {0, 0, 0, 0, 0, 0, 0};
             double uk[2] = {0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < 5; i++) xk[i] = p.X[((size_t)k * 5 + i) * Bm + b];
@@ -186,12 +206,13 @@ struct CtaSolver {
 #pragma unroll
             for (int i = 0; i < 5; i++) PP(i, k) = 0.0;
         }
-        // the obstacle chunks need the linearisation point and the (possibly shifted) initial v of their node
-        xk[0] = from_lead(xk[0]); xk[1] = from_lead(xk[1]);
-        const double v2 = from_lead(v[2]), v3 = from_lead(v[3]);
-        if (is_obst()) {
+        __syncthreads();
+        // the obstacle threads need the linearisation point and the (possibly shifted) initial v of their node
+        if (!node_warp() && is_obst()) {
             const int j = c - 1;
             const double sc = scal(k);
+            double xk[5] = {Q<PF_XU>(2), Q<PF_XU>(3), 0.0, 0.0, 0.0};
+            const double v2 = VV(2, k), v3 = VV(3, k);
             double hval, cx, cy;
             model_con_h(xk, p.P[((size_t)k * 2 * M + 2 * j) * Bm + b], p.P[((size_t)k * 2 * M + 2 * j + 1) * Bm + b], p.r2, &hval, &cx, &cy);
             const double s_l = p.SL[((size_t)k * M + j) * Bm + b], s_u = p.SU[((size_t)k * M + j) * Bm + b];
@@ -239,7 +260,7 @@ struct CtaSolver {
         double v[7] = {0, 0, 0, 0, 0, 0, 0}, sv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const double sc = scal(k);
         const double Zuq = sc * p.Zu;
-        if (is_lead()) {
+        if (node_warp() && is_lead()) {
             const double* Hd = k < N ? p.Hd : p.Hde;
 #pragma unroll
             for (int i = 0; i < 7; i++) { v[i] = VV(i, k); rg[i] = fma(Hd[i], v[i], Q<PF_G>(i)); Hx[i] = Hd[i] + p.reg_prim; }
@@ -287,11 +308,10 @@ struct CtaSolver {
                 slot_add(gt, s, fma(-fma(lu_, rdu, mu_), tiu, fma(ll, rdl, ml) * til));
             }
         }
-        // what the obstacle chunks need of their node
-        const double v2 = VV(2, k), v3 = VV(3, k);
         double o_rg2 = 0.0, o_rg3 = 0.0, o_h2 = 0.0, o_h3 = 0.0, o_hxy = 0.0, o_gt2 = 0.0, o_gt3 = 0.0;
-        if (is_obst()) {
+        if (!node_warp() && is_obst()) {
             const int j = c - 1;
+            const double v2 = VV(2, k), v3 = VV(3, k);
             const double vo2 = S(o.cv + 2, k), vo3 = S(o.cv + 3, k), dv2 = R<PF_DV>(2, k), dv3 = R<PF_DV>(3, k);
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
             double l0 = fma(a, Q<PF_DD>(i0), Q<PF_LAM>(i0)), l1 = fma(a, Q<PF_DD>(i1), Q<PF_LAM>(i1));
@@ -355,10 +375,16 @@ struct CtaSolver {
             const double coef = fma(-(Gl * rhol), Dli, q0) - fma(-(Gu * rhou), Dui, q1);
             o_gt2 = cx * coef; o_gt3 = cy * coef;
         }
-        o_rg2 = seg_sum(o_rg2); o_rg3 = seg_sum(o_rg3); o_h2 = seg_sum(o_h2); o_h3 = seg_sum(o_h3);
-        o_hxy = seg_sum(o_hxy); o_gt2 = seg_sum(o_gt2); o_gt3 = seg_sum(o_gt3);
-        if (is_lead()) {
-            rg[2] += o_rg2; rg[3] += o_rg3; Hx[2] += o_h2; Hx[3] += o_h3; hxy = o_hxy; gt[2] += o_gt2; gt[3] += o_gt3;
+        if (!node_warp()) {
+            o_rg2 = seg_sum(o_rg2); o_rg3 = seg_sum(o_rg3); o_h2 = seg_sum(o_h2); o_h3 = seg_sum(o_h3);
+            o_hxy = seg_sum(o_hxy); o_gt2 = seg_sum(o_gt2); o_gt3 = seg_sum(o_gt3);
+            if (is_obst() && c == 1) {
+                XCH(0) = o_rg2; XCH(1) = o_rg3; XCH(2) = o_h2; XCH(3) = o_h3; XCH(4) = o_hxy; XCH(5) = o_gt2; XCH(6) = o_gt3;
+            }
+        }
+        __syncthreads();
+        if (node_warp() && is_lead()) {
+            rg[2] += XCH(0); rg[3] += XCH(1); Hx[2] += XCH(2); Hx[3] += XCH(3); hxy = XCH(4); gt[2] += XCH(5); gt[3] += XCH(6);
             if (k < N) {
                 double rb[5];
                 b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
@@ -378,12 +404,12 @@ struct CtaSolver {
             }
         }
         double red[5] = {sum, n0, n1, n2, n3};
-        cta_reduce<1, 4, 0>(red);                            // (its barriers also order the reads of cv above ...
-        if (is_lead()) {
+        if (node_warp() && is_lead()) {                      // (the barrier above ordered the obstacle threads' reads of the old v in cv)
 #pragma unroll
-            for (int i = 0; i < 7; i++) S(o.cv + i, k) = Hx[i];   // ... against these stores of the node Hessian)
+            for (int i = 0; i < 7; i++) S(o.cv + i, k) = Hx[i];
             S(o.hg + 7, k) = hxy;
         }
+        cta_reduce<1, 4, 0>(red);
         sum_lt = red[0]; nrm[0] = red[1]; nrm[1] = red[2]; nrm[2] = red[3]; nrm[3] = red[4];
         mu = sum_lt / nc;
         __syncthreads();
@@ -393,8 +419,9 @@ struct CtaSolver {
     __device__ void riccati_factorize()
     {
         const int e = lane < 28 ? lane : 0;
-        int mi = 0;
-        while ((mi + 1) * (mi + 2) / 2 <= e) mi++;
+        // row of the packed lower triangle, branch-free: a `while` loop with a lane-dependent trip count left the lanes of
+        // the last row in a convergence group of their own for the whole factorisation (measured active mask 0xf01fffff)
+        const int mi = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21);
         const int mj = e - mi * (mi + 1) / 2;
         const int ai0 = lane / 5, aq0 = lane % 5, ai1 = (32 + lane) / 5, aq1 = (32 + lane) % 5;
         int ba0[5], ba1[5];
@@ -404,7 +431,7 @@ struct CtaSolver {
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
         const int xrow = xx ? o.lxx + b2_sym(mi - 2, mj - 2) : 0;
         const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
-        double* const scr = sm + o.total * NS;
+        double* const scr = sm + (o.total + PHI_ROWS) * NS;
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
             if (mi == mj) m = S(o.cv + mi, kk);
@@ -435,7 +462,13 @@ struct CtaSolver {
                 m += acc;
             }
             double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
+            // (unrolled: one problem per CTA is latency-bound, the compile-time shuffle lanes save the index arithmetic of the
+            //  rolled loop that the throughput kernel prefers for its instruction-cache footprint)
+#ifdef B2_CTA_ROLL_CHOL
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
             for (int cc = 0; cc < 7; cc++) {
                 const double pv_ = b2_bcast(m, cc * (cc + 1) / 2 + cc);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (cc <= mi ? cc : mi));
@@ -452,7 +485,9 @@ struct CtaSolver {
                     sigma *= pn;
                 }
             }
-            const double myrs = my_sp > 0.0 ? 1.0 / sqrt(my_sp) : 0.0;
+            // 1/sqrt(x) = sqrt(x) * (1/x): the square root and the reciprocal run side by side (both correctly rounded
+            // operations, like the mirror's), one multiplication after the slower of the two instead of a division after the root
+            const double myrs = my_sp > 0.0 ? sqrt(my_sp) * (1.0 / my_sp) : 0.0;
             m *= myrs;
             const double rs0 = b2_bcast(myrs, 0);
             const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double((1023 - (((__double2hiint(sp0) >> 20) & 0x7ff) - 1023)) << 20, 0) : 1.0;
@@ -496,51 +531,51 @@ struct CtaSolver {
         const double sc = scal(k);
         const double Zuq = sc * p.Zu;
         double gt[7] = {0, 0, 0, 0, 0, 0, 0};
-        double o2 = 0.0, o3 = 0.0;
-        if (kind == 3) {
+        if (!node_warp()) {
+            double o2 = 0.0, o3 = 0.0;
             if (is_obst()) {
                 const int j = c - 1;
                 const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
-                const double coef = fma(G1 * Q<PF_LRGSU>(j), Q<PF_DUI>(j), -((G0 * Q<PF_LRGSL>(j)) * Q<PF_DLI>(j)));
-                o2 = Q<PF_CX>(j) * coef; o3 = Q<PF_CY>(j) * coef;
-            }
-            o2 = seg_sum(o2); o3 = seg_sum(o3);
-            if (is_lead()) { S(o.hg + 2, k) += o2; S(o.hg + 3, k) += o3; }       // lin_residuals left lrg in hg
-        } else {
-            if (is_lead()) {
-                double v[7];
-#pragma unroll
-                for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
-#pragma unroll
-                for (int s = 0; s < 6; s++) {
-                    if (!box_on(s, k)) continue;
-                    const int il = o_lb + s, iu = o_ub + s;
-                    const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
-                    double lb, ub;
-                    box_bounds(s, lb, ub);
-                    const double vv = slot_get(v, s);
-                    const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
-                    const double ql = fma(ll, rdl, rm_of(ll, tl, Q<PF_DD>(il))) * Q<PF_TINV>(il);
-                    const double qu = fma(lu_, rdu, rm_of(lu_, tu, Q<PF_DD>(iu))) * Q<PF_TINV>(iu);
-                    slot_add(gt, s, ql - qu);
+                double coef;
+                if (kind == 3) {
+                    coef = fma(G1 * Q<PF_LRGSU>(j), Q<PF_DUI>(j), -((G0 * Q<PF_LRGSL>(j)) * Q<PF_DLI>(j)));
+                } else {
+                    double rhol, rhou, q0, q1;
+                    slack_rho(j, VV(2, k), VV(3, k), Zuq, sc, rhol, rhou, q0, q1);
+                    coef = fma(-(G0 * rhol), Q<PF_DLI>(j), q0) - fma(-(G1 * rhou), Q<PF_DUI>(j), q1);
                 }
-            }
-            if (is_obst()) {
-                const int j = c - 1;
-                double rhol, rhou, q0, q1;
-                slack_rho(j, VV(2, k), VV(3, k), Zuq, sc, rhol, rhou, q0, q1);
-                const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
-                const double coef = fma(-(G0 * rhol), Q<PF_DLI>(j), q0) - fma(-(G1 * rhou), Q<PF_DUI>(j), q1);
                 o2 = Q<PF_CX>(j) * coef; o3 = Q<PF_CY>(j) * coef;
             }
             o2 = seg_sum(o2); o3 = seg_sum(o3);
-            if (is_lead()) {
-                gt[2] += o2; gt[3] += o3;
+            if (is_obst() && c == 1) { XCH(0) = o2; XCH(1) = o3; }
+        } else if (is_lead() && kind != 3) {
+            double v[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (!box_on(s, k)) continue;
+                const int il = o_lb + s, iu = o_ub + s;
+                const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
+                double lb, ub;
+                box_bounds(s, lb, ub);
+                const double vv = slot_get(v, s);
+                const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
+                const double ql = fma(ll, rdl, rm_of(ll, tl, Q<PF_DD>(il))) * Q<PF_TINV>(il);
+                const double qu = fma(lu_, rdu, rm_of(lu_, tu, Q<PF_DD>(iu))) * Q<PF_TINV>(iu);
+                slot_add(gt, s, ql - qu);
+            }
+        }
+        __syncthreads();
+        if (node_warp() && is_lead()) {
+            if (kind == 3) { S(o.hg + 2, k) += XCH(0); S(o.hg + 3, k) += XCH(1); }       // lin_residuals left lrg in hg
+            else {
+                gt[2] += XCH(0); gt[3] += XCH(1);
 #pragma unroll
                 for (int i = 0; i < 7; i++) S(o.hg + i, k) = gt[i];
             }
         }
-        __syncthreads();
+        // (no block barrier: the node warp, which wrote hg, is the one that runs the sweeps next)
     }
 
     __device__ __forceinline__ void ctg_mul(int kk, const double* x, double* y) const
@@ -564,29 +599,75 @@ struct CtaSolver {
         }
     }
 
-    // backward + forward vector sweeps with the current factorisation (mpc_wpp.cuh riccati_solve()): the node-parallel
-    // products with the cost-to-go factor by the chunk-0 threads, the sequential cores by warp 0
+    // Feedback form of the factorisation, once per interior-point iteration (node-parallel, node warp):
+    //   G_k = Lxu Luu^-1 (5 x 2, stored over Lxu, which nothing reads afterwards),  Phi_k = A_k - B_k G_k^T (5 x 5).
+    // With them the sequential part of every KKT solve is one 5 x 5 matrix-vector product per node,
+    //   backward  p_k = c'_k + Phi_k^T p_{k+1},      c'_k = gx_k - G_k gu_k + Phi_k^T z_k,   z_k = P_{k+1} rb_k
+    //   forward   dx_{k+1} = f_k + Phi_k dx_k,        f_k = rb_k + B_k du0_k,  du0_k = -Luu^-T Luu^-1 (gu_k + B_k^T (p_{k+1} + z_k))
+    // and everything else (z, c', du0, f, du_k = du0_k - G_k^T dx_k, dpi_k = P_{k+1} dx_{k+1} + p_{k+1}) is node-parallel.
+    // Same mathematics as the substitution with the factor that mpc_wpp.cuh (and HPIPM) runs inside the sweep; the dependent
+    // chain per node shrinks from ~350 to ~100 cycles, which is what a latency-bound single problem needs.
+    // Node 0 has no G / Phi: its state is eliminated (dx_0 = 0, p_0 is never formed).
+    __device__ void feedback_matrices()
+    {
+        if (node_warp() && is_lead() && k >= 1 && k < N) {
+            const double l00i = S(o.lamu + 0, k), l10 = S(o.lamu + 1, k), l11i = S(o.lamu + 2, k);
+            double G0[5], G1[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                G1[i] = S(o.lxu + 2 * i + 1, k) * l11i;
+                G0[i] = fma(-G1[i], l10, S(o.lxu + 2 * i, k)) * l00i;
+                S(o.lxu + 2 * i, k) = G0[i]; S(o.lxu + 2 * i + 1, k) = G1[i];
+            }
+            const double h = p.dt, h2 = p.dt2h;
+            const double b00 = S(o.sv + SV_B00, k), b01 = S(o.sv + SV_B01, k), b10 = S(o.sv + SV_B10, k), b11 = S(o.sv + SV_B11, k);
+            const double a0[5] = {1.0, 0.0, S(o.sv + SV_A02, k), S(o.sv + SV_A03, k), S(o.sv + SV_A04, k)};
+            const double a1[5] = {0.0, 1.0, S(o.sv + SV_A12, k), S(o.sv + SV_A13, k), S(o.sv + SV_A14, k)};
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                S(PHI + 0 * 5 + j, k) = a0[j] - fma(b00, G0[j], b01 * G1[j]);
+                S(PHI + 1 * 5 + j, k) = a1[j] - fma(b10, G0[j], b11 * G1[j]);
+                S(PHI + 2 * 5 + j, k) = (j == 2 ? 1.0 : (j == 4 ? h : 0.0)) - h2 * G1[j];
+                S(PHI + 3 * 5 + j, k) = (j == 3 ? 1.0 : 0.0) - h * G0[j];
+                S(PHI + 4 * 5 + j, k) = (j == 4 ? 1.0 : 0.0) - h * G1[j];
+            }
+        }
+    }
+
+    // one KKT solve with the current factorisation in feedback form (see feedback_matrices()); kind 3 reads the linear
+    // residual (lrb) and writes the correction to cv / cpi.  Everything runs in the node warp: node-parallel phases with
+    // lane = node, the two sequential recursions with lanes 0..4 = vector components
     __device__ void riccati_solve(int kind)
     {
         const bool itr = (kind == 3);
         const int oRB = itr ? o.lrb : o.rb, oDV = itr ? o.cv : o.pf[PF_DV], oDPI = itr ? o.pf[PF_CPI] : o.pf[PF_DPI];
-        if (is_lead() && k < N) {
-            double rb[5], z[5];
+        const double h = p.dt, h2 = p.dt2h;
+        if (node_warp()) {
+            // ---- pre: z_k, c'_k
+            if (is_lead() && k < N) {
+                double rb[5], z[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
-            ctg_mul(k + 1, rb, z);
+                for (int i = 0; i < 5; i++) rb[i] = S(oRB + i, k);
+                ctg_mul(k + 1, rb, z);
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(oDPI + i, k) = z[i];                // z_k (overwritten by dpi_k below)
-        }
-        __syncthreads();
-        if (warp == 0) {
+                for (int i = 0; i < 5; i++) S(oDPI + i, k) = z[i];                // z_k (overwritten by dpi_k below)
+                if (k >= 1) {
+                    const double gu0 = S(o.hg + 0, k), gu1 = S(o.hg + 1, k);
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        double acc = S(o.hg + 2 + i, k) - fma(S(o.lxu + 2 * i, k), gu0, S(o.lxu + 2 * i + 1, k) * gu1);
+#pragma unroll
+                        for (int j = 0; j < 5; j++) acc = fma(S(PHI + j * 5 + i, k), z[j], acc);
+                        S(o.hg + 2 + i, k) = acc;
+                    }
+                }
+            }
+            __syncwarp();
+#ifdef B2_DEBUG_CLOCK
+            const long long c1_ = clock64();
+#endif
+            // ---- backward: p_k = c'_k + Phi_k^T p_{k+1}
             const int c5 = lane < 5 ? lane : 4;
-            int acol[5], arow[7];
-#pragma unroll
-            for (int r = 0; r < 5; r++) acol[r] = o.sv + B2_BATAB[r][2 + c5];
-#pragma unroll
-            for (int cc = 0; cc < 7; cc++) arow[cc] = o.sv + B2_BATAB[c5][cc];
-            const double h = p.dt, h2 = p.dt2h;
             double pf[5];
             {
                 const double pc = S(o.hg + 2 + c5, N);
@@ -594,54 +675,81 @@ struct CtaSolver {
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
             }
-            for (int kk = N - 1; kk >= 0; kk--) {
-                double s[5];
+            for (int kk = N - 1; kk >= 1; kk--) {
+                const double t01 = fma(S(PHI + 1 * 5 + c5, kk), pf[1], S(PHI + 0 * 5 + c5, kk) * pf[0]);
+                const double t23 = fma(S(PHI + 3 * 5 + c5, kk), pf[3], S(PHI + 2 * 5 + c5, kk) * pf[2]);
+                const double pc = (fma(S(PHI + 4 * 5 + c5, kk), pf[4], S(o.hg + 2 + c5, kk)) + t01) + t23;
+                if (lane < 5) R<PF_PV>(lane, kk) = pc;
 #pragma unroll
-                for (int r = 0; r < 5; r++) s[r] = pf[r] + S(oDPI + r, kk);
-                const double w0 = fma(S(o.sv + SV_B00, kk), s[0], S(o.hg + 0, kk)) + fma(S(o.sv + SV_B10, kk), s[1], h * s[3]);
-                const double w1 = fma(h, s[4], fma(S(o.sv + SV_B01, kk), s[0], S(o.hg + 1, kk)) + fma(S(o.sv + SV_B11, kk), s[1], h2 * s[2]));
-                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
+                for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
+            }
+#ifdef B2_DEBUG_CLOCK
+            clk_sweep += clock64() - c1_;
+#endif
+            __syncwarp();
+            // ---- mid: du0_k, f_k
+            if (is_lead() && k < N) {
+                double sx[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) sx[i] = R<PF_PV>(i, k + 1) + S(oDPI + i, k);
+                const double b00 = S(o.sv + SV_B00, k), b01 = S(o.sv + SV_B01, k), b10 = S(o.sv + SV_B10, k), b11 = S(o.sv + SV_B11, k);
+                const double w0 = fma(b00, sx[0], S(o.hg + 0, k)) + fma(b10, sx[1], h * sx[3]);
+                const double w1 = fma(h, sx[4], fma(b01, sx[0], S(o.hg + 1, k)) + fma(b11, sx[1], h2 * sx[2]));
+                const double l00i = S(o.lamu + 0, k), l10 = S(o.lamu + 1, k), l11i = S(o.lamu + 2, k);
                 const double lu0 = w0 * l00i;
                 const double lu1 = fma(-l10, lu0, w1) * l11i;
-                if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
-                if (kk > 0) {
-                    const double pa = fma(S(acol[0], kk), s[0], S(o.hg + 2 + c5, kk)) + fma(S(acol[1], kk), s[1], S(acol[2], kk) * s[2]);
-                    const double pb = fma(S(acol[3], kk), s[3], S(acol[4], kk) * s[4]);
-                    const double pc = (pa + pb) - fma(S(o.lxu + 2 * c5, kk), lu0, S(o.lxu + 2 * c5 + 1, kk) * lu1);
-                    if (lane < 5) R<PF_PV>(lane, kk) = pc;
-#pragma unroll
-                    for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
-                }
+                const double du1 = -lu1 * l11i;
+                const double du0 = fma(-l10, du1, -lu0) * l00i;
+                S(oDV + 0, k) = du0; S(oDV + 1, k) = du1;
+                S(oDV + 2 + 0, k + 1) = S(oRB + 0, k) + fma(b00, du0, b01 * du1);
+                S(oDV + 2 + 1, k + 1) = S(oRB + 1, k) + fma(b10, du0, b11 * du1);
+                S(oDV + 2 + 2, k + 1) = fma(h2, du1, S(oRB + 2, k));
+                S(oDV + 2 + 3, k + 1) = fma(h, du0, S(oRB + 3, k));
+                S(oDV + 2 + 4, k + 1) = fma(h, du1, S(oRB + 4, k));
             }
-            __syncwarp();
-            double dx[5] = {0, 0, 0, 0, 0};
             if (lane < 5) S(oDV + 2 + lane, 0) = 0.0;
-            for (int kk = 0; kk < N; kk++) {
-                double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
-                if (kk > 0) {
-                    r0 = fma(S(o.lxu + 2, kk), dx[1], fma(S(o.lxu + 0, kk), dx[0], r0)) + fma(S(o.lxu + 8, kk), dx[4], fma(S(o.lxu + 6, kk), dx[3], S(o.lxu + 4, kk) * dx[2]));
-                    r1 = fma(S(o.lxu + 3, kk), dx[1], fma(S(o.lxu + 1, kk), dx[0], r1)) + fma(S(o.lxu + 9, kk), dx[4], fma(S(o.lxu + 7, kk), dx[3], S(o.lxu + 5, kk) * dx[2]));
-                }
-                const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
-                const double du1 = -r1 * l11i;
-                const double du0 = fma(-l10, du1, -r0) * l00i;
-                const double xa = fma(S(arow[3], kk), dx[1], fma(S(arow[2], kk), dx[0], S(oRB + c5, kk))) + fma(S(arow[6], kk), dx[4], fma(S(arow[5], kk), dx[3], S(arow[4], kk) * dx[2]));
-                const double xn = xa + fma(S(arow[0], kk), du0, S(arow[1], kk) * du1);
-                if (lane == 0) { S(oDV + 0, kk) = du0; S(oDV + 1, kk) = du1; }
+            if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
+            __syncwarp();
+#ifdef B2_DEBUG_CLOCK
+            const long long c2_ = clock64();
+#endif
+            // ---- forward: dx_{k+1} = f_k + Phi_k dx_k  (dx_1 = f_0)
+            double dx[5];
+            {
+                const double xn = S(oDV + 2 + c5, 1);
+#pragma unroll
+                for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
+            }
+            for (int kk = 1; kk < N; kk++) {
+                const double t01 = fma(S(PHI + c5 * 5 + 1, kk), dx[1], S(PHI + c5 * 5 + 0, kk) * dx[0]);
+                const double t23 = fma(S(PHI + c5 * 5 + 3, kk), dx[3], S(PHI + c5 * 5 + 2, kk) * dx[2]);
+                const double xn = (fma(S(PHI + c5 * 5 + 4, kk), dx[4], S(oDV + 2 + c5, kk + 1)) + t01) + t23;
                 if (lane < 5) S(oDV + 2 + lane, kk + 1) = xn;
 #pragma unroll
                 for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
             }
-            if (lane == 0) { S(oDV + 0, N) = 0.0; S(oDV + 1, N) = 0.0; }
-        }
-        __syncthreads();
-        if (is_lead() && k < N) {
-            double dxn[5], y[5];
+#ifdef B2_DEBUG_CLOCK
+            clk_sweep += clock64() - c2_;
+#endif
+            __syncwarp();
+            // ---- post: du_k = du0_k - G_k^T dx_k, dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
+            if (is_lead() && k < N) {
+                if (k >= 1) {
+                    double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
-            ctg_mul(k + 1, dxn, y);
+                    for (int i = 0; i < 5; i++) {
+                        const double dxi = S(oDV + 2 + i, k);
+                        d0 = fma(S(o.lxu + 2 * i, k), dxi, d0); d1 = fma(S(o.lxu + 2 * i + 1, k), dxi, d1);
+                    }
+                    S(oDV + 0, k) -= d0; S(oDV + 1, k) -= d1;
+                }
+                double dxn[5], y[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) S(oDPI + i, k) = y[i] + R<PF_PV>(i, k + 1);
+                for (int i = 0; i < 5; i++) dxn[i] = S(oDV + 2 + i, k + 1);
+                ctg_mul(k + 1, dxn, y);
+#pragma unroll
+                for (int i = 0; i < 5; i++) S(oDPI + i, k) = y[i] + R<PF_PV>(i, k + 1);
+            }
         }
         __syncthreads();
     }
@@ -662,25 +770,7 @@ struct CtaSolver {
         const double sc = scal(k);
         const double Zuq = sc * p.Zu;
         const bool keep_dd = (MODE == XP_SOLVE) && kind == 0 && p.pred_corr;
-        if (MODE == XP_REFINE) {
-            // dv += cv, dpi += cpi: every chunk reads what it needs of the old rows first
-            double dvn[7] = {0, 0, 0, 0, 0, 0, 0};
-            if (is_lead()) {
-#pragma unroll
-                for (int i = 0; i < 7; i++) dvn[i] = R<PF_DV>(i, k) + S(o.cv + i, k);
-            }
-            __syncwarp();
-            if (is_lead()) {
-#pragma unroll
-                for (int i = 0; i < 7; i++) R<PF_DV>(i, k) = dvn[i];
-                if (k < N) {
-#pragma unroll
-                    for (int i = 0; i < 5; i++) R<PF_DPI>(i, k) += R<PF_CPI>(i, k);
-                }
-            }
-            __syncwarp();
-        }
-        if (is_lead()) {
+        if (node_warp() && is_lead()) {
             double v[7], dv[7], cv[7];
 #pragma unroll
             for (int i = 0; i < 7; i++) { v[i] = VV(i, k); dv[i] = R<PF_DV>(i, k); cv[i] = MODE == XP_REFINE ? S(o.cv + i, k) : 0.0; }
@@ -712,7 +802,7 @@ struct CtaSolver {
                 if (MODE == XP_LIN) slot_add(lrg, s, -dll + dlu);
             }
         }
-        if (is_obst()) {
+        if (!node_warp() && is_obst()) {
             const int j = c - 1;
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
             const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
@@ -781,8 +871,29 @@ struct CtaSolver {
     {
         rm_cdd = kind == 1 ? 1.0 : 0.0;
         rm_smu = kind == 0 ? 0.0 : smu;
+#ifdef B2_DEBUG_CLOCK
+        const long long cp_ = clock64();
+#endif
         if (kind != 0) solve_prep(kind);
+#ifdef B2_DEBUG_CLOCK
+        const long long cr_ = clock64(); clk_prep += cr_ - cp_;
+#endif
         riccati_solve(kind);
+#ifdef B2_DEBUG_CLOCK
+        const long long ce_ = clock64(); clk_rs += ce_ - cr_;
+#endif
+        if (kind == 3) {
+            // add the refinement correction to the stored step before anybody expands it: dv += cv, dpi += cpi
+            if (node_warp() && is_lead()) {
+#pragma unroll
+                for (int i = 0; i < 7; i++) R<PF_DV>(i, k) += S(o.cv + i, k);
+                if (k < N) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) R<PF_DPI>(i, k) += R<PF_CPI>(i, k);
+                }
+            }
+            __syncthreads();
+        }
         double s1 = 0.0, s2 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0;
         ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
         if (kind == 3) expand<XP_REFINE>(3, s1, s2, nullptr, d0, d1, d2);
@@ -793,6 +904,9 @@ struct CtaSolver {
         S1 = red[0]; S2 = red[1];
         alpha = -(red[2] > red[3] ? red[2] : red[3]);
         __syncthreads();
+#ifdef B2_DEBUG_CLOCK
+        clk_exp += clock64() - ce_;
+#endif
     }
 
     // residual of the linear system at the stored step; leaves lrg in rows hg[0..6] and lrb in rows lrb[0..4]
@@ -800,7 +914,7 @@ struct CtaSolver {
     {
         double ln0 = 0.0, ln1 = 0.0, o2 = 0.0, o3 = 0.0, s1 = 0.0, s2 = 0.0;
         double lrg[7] = {0, 0, 0, 0, 0, 0, 0}, dv[7] = {0, 0, 0, 0, 0, 0, 0}, sv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (is_lead()) {
+        if (node_warp() && is_lead()) {
             const double* Hd = k < N ? p.Hd : p.Hde;
 #pragma unroll
             for (int i = 0; i < 7; i++) { dv[i] = R<PF_DV>(i, k); lrg[i] = fma(Hd[i], dv[i], Q<PF_RG>(i)); }
@@ -820,9 +934,13 @@ struct CtaSolver {
             }
         }
         expand<XP_LIN>(0, s1, s2, lrg, o2, o3, ln0);
-        o2 = seg_sum(o2); o3 = seg_sum(o3);
-        if (is_lead()) {
-            lrg[2] += o2; lrg[3] += o3;
+        if (!node_warp()) {
+            o2 = seg_sum(o2); o3 = seg_sum(o3);
+            if (is_obst() && c == 1) { XCH(0) = o2; XCH(1) = o3; }
+        }
+        __syncthreads();
+        if (node_warp() && is_lead()) {
+            lrg[2] += XCH(0); lrg[3] += XCH(1);
             if (k < N) {
                 double lrb[5];
                 b2_ba_mul(sv, p.dt, p.dt2h, dv, lrb);
@@ -848,16 +966,31 @@ struct CtaSolver {
     __device__ void run()
     {
         int status = 0, qs = 0, n_itref = 0;
+#ifdef B2_DEBUG_CLOCK
+        const long long call0_ = clock64();
+#endif
         prepare_and_init();
         alpha = 1.0;
         int kk = 0;
         const double inv_nc = 1.0 / nc;
         double a = 0.0;
         for (;; kk++) {
+#ifdef B2_DEBUG_CLOCK
+            const long long ch_ = clock64();
+#endif
             head(a);
+#ifdef B2_DEBUG_CLOCK
+            clk_head += clock64() - ch_;
+#endif
             if (!(kk < p.qp_iter_max && alpha > p.alpha_min &&
                   (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max))) break;
-            if (warp == 0) riccati_factorize();
+#ifdef B2_DEBUG_CLOCK
+            const long long c0_ = clock64();
+#endif
+            if (node_warp()) { riccati_factorize(); feedback_matrices(); }
+#ifdef B2_DEBUG_CLOCK
+            clk_fact += clock64() - c0_;
+#endif
             __syncthreads();
             int kind = 0, itref = 0;
             double smu = 0.0, mu_aff0 = 0.0;
@@ -879,7 +1012,13 @@ struct CtaSolver {
                 }
                 if (itref >= p.itref_corr_max) break;
                 double lnrm[2];
+#ifdef B2_DEBUG_CLOCK
+                const long long cl_ = clock64();
+#endif
                 lin_residuals(lnrm);
+#ifdef B2_DEBUG_CLOCK
+                clk_lin += clock64() - cl_;
+#endif
                 if (lnrm[0] < p.res_g_max && lnrm[1] < p.res_b_max) break;
                 kind = 3; itref++; n_itref++;
             }
@@ -892,7 +1031,7 @@ struct CtaSolver {
         else qs = 0;
         status = (qs != 0 && qs != 1) ? 4 : 0;     // ACADOS_QP_FAILURE leaves the iterate and the multipliers untouched
         if (status == 0) {
-            if (is_lead()) {
+            if (node_warp() && is_lead()) {
 #pragma unroll
                 for (int i = 0; i < 5; i++) p.X[((size_t)k * 5 + i) * Bm + b] += VV(2 + i, k);
                 if (k < N) {
@@ -907,7 +1046,7 @@ struct CtaSolver {
                     p.T[((size_t)k * nct + o_lb + s) * Bm + b] = Q<PF_T>(o_lb + s); p.T[((size_t)k * nct + o_ub + s) * Bm + b] = Q<PF_T>(o_ub + s);
                 }
             }
-            if (is_obst()) {
+            if (!node_warp() && is_obst()) {
                 const int j = c - 1;
                 p.SL[((size_t)k * M + j) * Bm + b] += Q<PF_SL>(j);
                 p.SU[((size_t)k * M + j) * Bm + b] += Q<PF_SU>(j);
@@ -919,17 +1058,40 @@ struct CtaSolver {
                 }
             }
         }
+#ifdef B2_DEBUG_CLOCK
+        clk_all = clock64() - call0_;
+        if (tid == NODE_WARP * 32) {
+            p.STATS[5 * Bm + b] = (double)clk_fact; p.STATS[6 * Bm + b] = (double)clk_sweep; p.STATS[7 * Bm + b] = (double)clk_all;
+            p.STATS[0 * Bm + b] = (double)clk_head; p.STATS[1 * Bm + b] = (double)clk_prep; p.STATS[2 * Bm + b] = (double)clk_rs;
+            p.STATS[3 * Bm + b] = (double)clk_exp; p.STATS[4 * Bm + b] = (double)clk_lin;
+        }
+        if (tid != 0 || true) {}
+#endif
         if (tid == 0) {
             p.STATUS[b] = status; p.QP_ITER[b] = kk; p.QP_STATUS[b] = qs;
+#ifndef B2_DEBUG_CLOCK
             p.STATS[0 * Bm + b] = nrm[0]; p.STATS[1 * Bm + b] = nrm[1]; p.STATS[2 * Bm + b] = nrm[2]; p.STATS[3 * Bm + b] = nrm[3];
-            p.STATS[4 * Bm + b] = mu; p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
+            p.STATS[4 * Bm + b] = mu;
+#endif
+#ifndef B2_DEBUG_CLOCK
+            p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
+#endif
         }
         __syncthreads();
     }
 };
 
+#ifndef B2_CTA_MINB
+#define B2_CTA_MINB 3           // resident CTAs per SM the kernel is compiled for (61 KB of shared memory per problem at N = 20: 3 fit)
+#endif
+// dynamic shared memory of the CTA kernel: the all-shared layout of mpc_wpp.cuh + the Phi rows
+__host__ __device__ inline size_t b2_cta_smem_bytes(int N, int M)
+{
+    return b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED) + sizeof(double) * 25 * (size_t)b2_wpp_stride(N);
+}
+
 template <int MT, int NT>
-__global__ void __launch_bounds__(CtaSolver<MT, NT>::NTHR, 4) b2_rti_solve_cta(const B2Params p)
+__global__ void __launch_bounds__(CtaSolver<MT, NT>::NTHR, B2_CTA_MINB) b2_rti_solve_cta(const B2Params p)
 {
     B2_DYNAMIC_SMEM(double, b2_smem);
     __shared__ int s_next;

@@ -755,6 +755,9 @@ struct WppSolver {
             for (int i = 0; i < 5; i++) rDPI(i, k) = z[i];                // z_k (overwritten by dpi_k below)
         }
         __syncwarp();
+#ifdef B2_DEBUG_CLOCK
+        const long long c1_ = clock64();
+#endif
         const int c5 = lane < 5 ? lane : 4;
         int acol[5], arow[7];
 #pragma unroll
@@ -825,6 +828,9 @@ struct WppSolver {
         }
         if (lane == 0) { rDV(0, N) = 0.0; rDV(1, N) = 0.0; }
         __syncwarp();
+#ifdef B2_DEBUG_CLOCK
+        clk_sweep += clock64() - c1_;
+#endif
         for (k = lane; k < N; k += 32) {
             double dxn[5], y[5];
 #pragma unroll
@@ -958,6 +964,9 @@ struct WppSolver {
     // running "most limiting" ratios lam/dlam and t/dt (HPIPM d_compute_alpha_qp, negative-reciprocal
     // convention) kept as numerator/denominator pairs: one division per lane at the end
     double ad_n, ad_d, ap_n, ap_d;
+#ifdef B2_DEBUG_CLOCK
+    long long clk_fact = 0, clk_sweep = 0, clk_all = 0;
+#endif
 
     template <int MODE>
     __device__ __forceinline__ void consume(int i, double l, double t, double dti, double dli, double a,
@@ -1209,6 +1218,9 @@ struct WppSolver {
     {
         int sqp_it = 0, qp_total = 0, status = 0, qs = 0, n_itref = 0;
         double nres[4] = {0.0, 0.0, 0.0, 0.0}, last_al = 1.0;
+#ifdef B2_DEBUG_CLOCK
+        const long long call0_ = clock64();
+#endif
         for (;;) {
         prepare_and_init();
         if (SQP) {
@@ -1224,7 +1236,13 @@ struct WppSolver {
             head(a);
             if (!(kk < p.qp_iter_max && alpha > p.alpha_min &&
                   (nrm[0] > p.res_g_max || nrm[1] > p.res_b_max || nrm[2] > p.res_d_max || nrm[3] > p.res_m_max))) break;
+#ifdef B2_DEBUG_CLOCK
+            const long long c0_ = clock64();
+#endif
             riccati_factorize();
+#ifdef B2_DEBUG_CLOCK
+            clk_fact += clock64() - c0_;
+#endif
             // predictor, corrector, (conditional) centering, <= itref_corr_max refinement steps
             int kind = 0, itref = 0;
             double smu = 0.0, mu_aff0 = 0.0;
@@ -1322,6 +1340,9 @@ struct WppSolver {
             p.STATUS[b] = status; p.QP_ITER[b] = qp_total; p.QP_STATUS[b] = qs;
             p.STATS[0 * Bm + b] = nrm[0]; p.STATS[1 * Bm + b] = nrm[1]; p.STATS[2 * Bm + b] = nrm[2]; p.STATS[3 * Bm + b] = nrm[3];
             p.STATS[4 * Bm + b] = mu; p.STATS[5 * Bm + b] = alpha; p.STATS[6 * Bm + b] = (double)n_itref; p.STATS[7 * Bm + b] = 0.0;
+#ifdef B2_DEBUG_CLOCK
+            p.STATS[5 * Bm + b] = (double)clk_fact; p.STATS[6 * Bm + b] = (double)clk_sweep; p.STATS[7 * Bm + b] = (double)(clock64() - call0_);
+#endif
             if (SQP) {
                 p.STATS[7 * Bm + b] = last_al;
                 p.SQP_ITER[b] = sqp_it;

@@ -93,7 +93,7 @@ int b2mirror_solve(const b2mpc_config* cfg, int layout, int sqp, int64_t B, int 
 #define RUN(MT, NT, SM) do { if (sqp) run_kernel<MT, NT, SM, true>(prm, grid, smem, host_threads); \
                              else run_kernel<MT, NT, SM, false>(prm, grid, smem, host_threads); } while (0)
     if (layout == 4) {
-        const size_t smem4 = b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED);
+        const size_t smem4 = b2_cta_smem_bytes(N, M);
         if (N == 20) simt::run_grid(grid, CtaSolver<5, 20>::NTHR, smem4, host_threads, [&]() { b2_rti_solve_cta<5, 20>(prm); });
         else simt::run_grid(grid, CtaSolver<5, 10>::NTHR, smem4, host_threads, [&]() { b2_rti_solve_cta<5, 10>(prm); });
     }

@@ -1,8 +1,9 @@
 """Summarise one `ncu --set full --import-source on` capture of the warp kernel into markdown (profiles/*.md).
-usage: ncu_summary.py <report.ncu-rep> <lib.so> <kernel-symbol> <title> > out.md
+usage: ncu_summary.py <report.ncu-rep> <lib.so> <kernel-symbol> <title> [source file under csrc/, default mpc_wpp.cuh] > out.md
 Needs ncu, cuobjdump and nvdisasm on PATH (no GPU)."""
 import csv, glob, io, os, subprocess, sys, tempfile
 rep, lib, sym, title = sys.argv[1:5]
+src_name = sys.argv[5] if len(sys.argv) > 5 else "mpc_wpp.cuh"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -35,7 +36,7 @@ with tempfile.TemporaryDirectory() as td:
     dis = os.path.join(td, "dis.txt")
     open(dis, "w").write(subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_stalls_by_func.py"), sass, dis, sym,
-                          os.path.join(ROOT, "dynamic-obstacle-avoidance-mpc_b200", "csrc", "mpc_wpp.cuh")], capture_output=True, text=True).stdout
+                          os.path.join(ROOT, "dynamic-obstacle-avoidance-mpc_b200", "csrc", src_name)], capture_output=True, text=True).stdout
 print("\n## pc samples per source function, split by stall reason (% of all samples; ncu SASS page joined with nvdisasm line info)\n\n```")
 print(out.rstrip())
 print("```")

@@ -79,3 +79,32 @@ def test_mirror_matches_independent_oracle(mirror, oracle, N, M, tf, B, qp_iter_
         assert _rel_rows(m[k], r[k])[sel].max() < 1e-6, k
     for k in ("lam", "t", "pi"):
         assert _rel_rows(out[k], d[k])[sel].max() < 1e-5, k
+
+
+@pytest.mark.parametrize("N,tf,B", [(20, 2.0, 64), (10, 1.0, 48)])
+def test_cta_kernel_mirror_matches_oracle_and_warp_kernel(mirror, oracle, N, tf, B):
+    """the CTA-per-problem latency kernel (csrc/mpc_cta.cuh: 160-thread blocks, obstacle warps + node warp, feedback-form
+    sweeps), executed by the emulator with block barriers and multi-warp reductions: the independent oracle's tolerance,
+    and agreement with the warp-per-problem kernel to rounding"""
+    dims = world.MpcDims(N, 5, tf)
+    sc = world.random_scenarios(B, dims, seed=2, moving_start=True)
+    cfg = mirror.default_config(N, 5, tf)
+    res = {}
+    for layout in (4, 2):
+        m = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+        out = mirror.solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], m["x"], m["u"], m["sl"], m["su"], layout=layout)
+        res[layout] = (m, out)
+    r = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    d = {}
+    st, it, _ = oracle.rti_solve_batch(oracle.default_config(N, 5, tf), sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"],
+                                       r["x"], r["u"], r["sl"], r["su"], nthreads=4, duals=d)
+    m4, o4 = res[4]
+    assert (o4["status"] == st).all() and np.mean(o4["qp_iter"] == it) >= 0.95 and np.abs(o4["qp_iter"] - it).max() <= 1
+    sel = (st == 0) & (it < 50) & (o4["qp_iter"] < 50)
+    assert sel.mean() > 0.4
+    for k in ("u", "x"):
+        assert _rel_rows(m4[k], r[k])[sel].max() < 1e-6, k
+        assert _rel_rows(m4[k], res[2][0][k])[sel].max() < 1e-6, k
+    for k in ("lam", "pi"):
+        assert _rel_rows(o4[k], d[k])[sel].max() < 1e-5, k
+    assert np.mean(o4["qp_iter"] == res[2][1]["qp_iter"]) >= 0.95
