@@ -918,6 +918,13 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
         if (tol4) for (int i = 0; i < 4; i++) p.nlp_tol[i] = tol4[i];
     }
     B2Order o(h);
+    if (batch == 1) {
+        // one problem: nothing to order -- the work counter is all the solve kernel needs (two launches less on the
+        // single-episode latency path)
+        CUDA_TRY(cudaMemsetAsync(o.next, 0, 2 * sizeof(int32_t), st));
+        p.ORDER = nullptr; p.NEXT = o.next; p.NQ = nullptr;
+        return launch_solve(h, p, batch, sqp, st);
+    }
     CUDA_TRY(cudaMemsetAsync(o.hist[0], 0, (4 * B2_ORDER_MAXKEYS + 8) * sizeof(int32_t), st));
     const unsigned ob = (unsigned)((batch + 127) / 128);
     b2_order_keys<<<ob, 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], o.key, o.hist[0], h->N, h->M, h->cfg.r2, (int)batch, h->Bm);

@@ -21,6 +21,8 @@
 #pragma once
 #include "mpc_wpp.cuh"
 
+#define B2_CTA_PHI_ROWS 25       // rows appended to the all-shared layout of mpc_wpp.cuh: the entries of Phi_k (feedback form)
+
 template <int MT, int NT>
 struct CtaSolver {
     static constexpr unsigned long long SMASK = B2_WPP_ALL_SHARED;
@@ -31,7 +33,7 @@ struct CtaSolver {
     static constexpr int NWARPS = NOW + 1;
     static constexpr int NTHR = 32 * NWARPS;
     static_assert(MT >= 1 && MT <= 8 && NT + 1 <= 32 && NWARPS <= 8, "CTA kernel: M <= 8, N <= 31");
-    static constexpr int PHI_ROWS = 25;                     // Phi_k of the feedback form, appended to the all-shared layout
+    static constexpr int PHI_ROWS = B2_CTA_PHI_ROWS;                     // Phi_k of the feedback form, appended to the all-shared layout
     static constexpr int o_lb = 0, o_lg = 6, o_ub = 6 + MT, o_ug = 12 + MT, o_ls = 12 + 2 * MT, o_us = 12 + 3 * MT;
 
     const B2Params& p;
@@ -634,6 +636,9 @@ struct CtaSolver {
         }
     }
 
+    // (Experiment, negative: every lane carrying the whole 5-vector with all 25 entries of Phi as broadcast loads -- no shuffle
+    //  on the chain -- measured 2.1x SLOWER sweeps (38.6 k vs 18.3 k cycles per iteration): 25 FP64 operations per node and
+    //  lane on a half-rate pipe cost more than the 26-cycle broadcast they avoid.)
     // one KKT solve with the current factorisation in feedback form (see feedback_matrices()); kind 3 reads the linear
     // residual (lrb) and writes the correction to cv / cpi.  Everything runs in the node warp: node-parallel phases with
     // lane = node, the two sequential recursions with lanes 0..4 = vector components
@@ -1082,12 +1087,13 @@ struct CtaSolver {
 };
 
 #ifndef B2_CTA_MINB
-#define B2_CTA_MINB 3           // resident CTAs per SM the kernel is compiled for (61 KB of shared memory per problem at N = 20: 3 fit)
+#define B2_CTA_MINB 2           // resident CTAs per SM the kernel is compiled for: 168 registers.  (61 KB of shared memory per problem
+                                // would allow 3 at 128 registers: measured 6.5 % slower per problem, 1.426 vs 1.333 ms)
 #endif
 // dynamic shared memory of the CTA kernel: the all-shared layout of mpc_wpp.cuh + the Phi rows
 __host__ __device__ inline size_t b2_cta_smem_bytes(int N, int M)
 {
-    return b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED) + sizeof(double) * 25 * (size_t)b2_wpp_stride(N);
+    return b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED) + sizeof(double) * B2_CTA_PHI_ROWS * (size_t)b2_wpp_stride(N);
 }
 
 template <int MT, int NT>

@@ -25,6 +25,9 @@
  *     b2mpc_last_error().  Per-problem numerical status uses acados codes (0 ok, 4 QP failure).
  *   - a handle is not thread-safe; no call synchronises the stream unless documented.
  *   - there is NO CPU fallback: without a CUDA device b2mpc_create fails.
+ *   - obstacle constraints are SOFT on both sides (Jsh = I, robot_ocp_problem.py:106-122, the `slack=True` every experiment of
+ *     the reference uses).  The hard-constraint variant (`RobotOcpProblem(..., slack=False)`, :14) is not part of the
+ *     accelerated path: the Python mirror raises NotImplementedError for it.
  */
 #ifndef B200MPC_H
 #define B200MPC_H
@@ -47,7 +50,10 @@ typedef struct b2mpc_config {
     int32_t n_obst;          /* N_OBST, world_specification.py:25; 1..B2MPC_MAX_OBST */
     int32_t device;          /* CUDA ordinal */
     int32_t max_batch;       /* independent problems per solve */
-    int32_t integrator;      /* 0 = IRK Gauss-Legendre-4 (reference, :129), 1 = RK4 */
+    int32_t integrator;      /* 0 = IRK Gauss-Legendre-4 (reference, :129; the closed form of the collocation system, which
+                                the model generator derives AND checks against the IRK equations: codegen/gen_model.py
+                                verify_collocation; a model whose ODE is not triangular is rejected at generation time --
+                                there is no generic on-device IRK-Newton), 1 = RK4 */
     int32_t qp_iter_max;     /* solver_options.qp_solver_iter_max, :131 */
     int32_t lm_scaled_by_dt; /* acados-version switch for levenberg_marquardt scaling */
     int32_t kernel;          /* 0 = auto (2; batches that fit the GPU in one wave: 3), 2 = warp-per-problem with the node-private

@@ -72,7 +72,7 @@ struct Cta {
     int nthreads = 0, live = 0, cur = 0;
     uint3_ bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
     char* smem = nullptr;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_used = 0;
     Barrier warp_bar[MAX_WARPS];
     Barrier sub_bar[MAX_WARPS][4];               // partial-mask collectives: keyed by the lowest lane of the mask / 8
     Barrier cta_bar, named[N_NAMED];
@@ -208,7 +208,8 @@ void run_block(Cta& c, const std::function<void()>& body, uint3_ bid, uint3_ gdi
         c.smem_bytes = smem_bytes + 1024;
         if (posix_memalign((void**)&c.smem, 128, c.smem_bytes)) abort();
     }
-    memset(c.smem, 0xA5, c.smem_bytes);            // uninitialised shared memory is garbage on the GPU, too
+    memset(c.smem, 0xA5, c.smem_bytes);            // uninitialised shared memory is garbage on the GPU, too (and the
+    c.smem_used = smem_bytes;                      // bytes past the launch's size are a canary, checked after the block)
     for (auto& b : c.warp_bar) { b.arrived = 0; }
     for (auto& w : c.sub_bar) for (auto& b : w) b.arrived = 0;
     c.cta_bar.arrived = 0;
@@ -229,6 +230,12 @@ void run_block(Cta& c, const std::function<void()>& body, uint3_ bid, uint3_ gdi
     g_lane = &c.lanes[0];
     simt_switch(&c.sched_sp, c.lanes[0].sp);
     g_cta = nullptr;
+    for (size_t i = c.smem_used; i < c.smem_bytes; i++) {
+        if ((unsigned char)c.smem[i] != 0xA5) {
+            fprintf(stderr, "simt_emu: block (%u,%u,%u) wrote shared memory at byte %zu, past the %zu bytes of the launch\n", bid.x, bid.y, bid.z, i, c.smem_used);
+            abort();
+        }
+    }
 }
 #endif
 
