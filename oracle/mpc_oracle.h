@@ -19,6 +19,12 @@
  * (src/simulation/test_data, 8 settings x 100 seeded episodes) are reproduced per seed
  * by the same algorithm on the GPU (54-63 % of the episodes
  * identical at QP_ITER = 100) -- the iterates of a single solve() remain unpinned.
+ * Round 2: HPIPM's lq_fact switch is restated here too (orc_config.lq_fact) and replayed against
+ * those recordings: no effect beyond their noise.
+ *
+ * This is the INDEPENDENT checker (different code, plain Cholesky, sequential sums, libm sincos);
+ * the bit-exact checker of the CUDA kernels is the mirror under oracle/simt/ (the kernel source
+ * compiled for the CPU).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The CUDA product never links it.

@@ -138,3 +138,31 @@ def test_glue_shift_and_initial_guess(oracle):
     oracle.initial_guess(cfg, x0, x, u, sl, su)
     assert np.array_equal(x0, [1, 2, 0.3, 0, 0])                   # aliasing quirk, :301-302
     assert (x == x0).all() and (u == 0).all() and (sl == 0).all() and (su == 0).all()
+
+
+def test_lq_fact_variants_agree(oracle):
+    """HPIPM's lq_fact switch restated in the oracle (round 2): 0 = Cholesky of the summed node matrix, 1 = switch
+    to the LQ-based factorisation when the predictor's linear residual exceeds 1e-5 (mode BALANCE), 2 = LQ always.  The LQ
+    factor of [chol(H) | sqrt(Gamma_b) | C sqrt(Gamma_g) | AL] is the Cholesky factor of the same node matrix, so the three
+    variants walk the same interior-point path up to rounding: same solutions on converged QPs, iteration counts equal but
+    for the +-1 of the exit test."""
+    from b200mpc import world
+    dims = world.MpcDims(20, 5, 2.0)
+    B = 96
+    sc = world.random_scenarios(B, dims, seed=7, moving_start=True)
+    res = {}
+    for lq in (0, 1, 2):
+        cfg = oracle.default_config(20, 5, 2.0, lq_fact=lq)
+        it_ = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+        st, it, stats = oracle.rti_solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], it_["x"], it_["u"], it_["sl"], it_["su"], nthreads=4)
+        res[lq] = (it_, st, it, stats)
+    assert (res[0][3][:, 7] == 0).all()                      # stats[7]: iterations that ran on the LQ factorisation
+    assert (res[2][3][:, 7] == res[2][2]).all()              # lq_fact = 2: all of them
+    sw = res[1][3][:, 7] > 0
+    assert 0.1 < sw.mean() < 0.9                             # mode BALANCE switches on a good part of the cold problems, not on all
+    for lq in (1, 2):
+        assert (res[lq][1] == res[0][1]).all()
+        assert np.mean(res[lq][2] == res[0][2]) >= 0.95 and np.abs(res[lq][2] - res[0][2]).max() <= 2
+        conv = (res[lq][2] < 50) & (res[0][2] < 50) & (res[0][1] == 0)
+        du = np.abs(res[lq][0]["u"] - res[0][0]["u"]).reshape(B, -1).max(1)
+        assert conv.mean() > 0.4 and du[conv].max() < 1e-6
