@@ -23,12 +23,17 @@
 
 #define B2_CTA_PHI_ROWS 25       // rows appended to the all-shared layout of mpc_wpp.cuh: the entries of Phi_k (feedback form)
 
-template <int MT, int NT>
+// NOW_: obstacle warps per problem (0 = one (node, obstacle) pair per thread: ceil((N+1) / (32/M)) warps, the latency
+// configuration; fewer warps walk the pairs in rounds).  SMASK_: placement of the node-private fields as in mpc_wpp.cuh
+// (B2_WPP_ALL_SHARED: everything in shared memory; B2_WPP_ALL_GLOBAL: the private rows in a per-CTA block of L2-resident
+// global memory, which is what lets 8-10 problems share an SM).
+template <int MT, int NT, int NOW_ = 0, unsigned long long SMASK_ = B2_WPP_ALL_SHARED>
 struct CtaSolver {
-    static constexpr unsigned long long SMASK = B2_WPP_ALL_SHARED;
-    static constexpr int M = MT, N = NT, NS = (NT + 1) | 1, nct = 12 + 4 * MT;
-    static constexpr int NPW = 32 / MT;                     // nodes per obstacle warp
-    static constexpr int NOW = (NT + 1 + NPW - 1) / NPW;    // obstacle warps
+    static constexpr unsigned long long SMASK = SMASK_;
+    static constexpr int M = MT, N = NT, NS = (NT + 1) | 1, GS = NT + 1, nct = 12 + 4 * MT;
+    static constexpr int NPW = 32 / MT;                     // nodes per obstacle warp and round
+    static constexpr int NOW = NOW_ > 0 ? NOW_ : (NT + 1 + NPW - 1) / NPW;    // obstacle warps
+    static constexpr int OROUNDS = (NT + 1 + NPW * NOW - 1) / (NPW * NOW);    // rounds in which they walk the (node, obstacle) pairs
     static constexpr int NODE_WARP = NOW;                   // the node warp (also runs the sequential sweeps)
     static constexpr int NWARPS = NOW + 1;
     static constexpr int NTHR = 32 * NWARPS;
@@ -39,12 +44,13 @@ struct CtaSolver {
     const B2Params& p;
     const int b, tid, lane, warp;
     double* const sm;
+    double* const gm;       // this CTA's block of node-private rows in global memory (fields whose SMASK bit is clear)
     const WOff o;
     const int PHI;          // first of the 25 rows of Phi
     const size_t Bm;
     const int c;            // obstacle warps: 1 + obstacle index of this thread; node warp: 0
-    const bool act;         // the thread owns a node (node warp) or a (node, obstacle) pair (obstacle warps)
-    const int k;            // its node (clamped into range for idle threads)
+    bool act;               // the thread owns a node (node warp) or, in the current round, a (node, obstacle) pair (obstacle warps)
+    int k;                  // its node (clamped into range for idle threads)
     int nc;
     double mu, nrm[4], sum_lt, alpha, S1, S2;
     double rm_cdd, rm_smu;
@@ -53,31 +59,46 @@ struct CtaSolver {
     long long clk_fact = 0, clk_sweep = 0, clk_all = 0, clk_head = 0, clk_prep = 0, clk_rs = 0, clk_exp = 0, clk_lin = 0;
 #endif
 
-    __device__ CtaSolver(const B2Params& p_, int b_, double* sm_)
+    __device__ CtaSolver(const B2Params& p_, int b_, double* sm_, double* gm_)
         : p(p_), b(b_), tid(threadIdx.x), lane(threadIdx.x & 31),
           // the warp index through a shuffle: tells the compiler that it is WARP-UNIFORM, so that `if (warp == 0)` around the
           // sweeps is a uniform branch and the shuffles inside are compiled for a converged warp (without it every shuffle
           // of the factorisation went through the divergent-warp path: WARPSYNC.COLLECTIVE per SHFL, 7x slower sweeps)
-          warp(__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0)), sm(sm_), o(MT, SMASK, false),
-          PHI(WOff(MT, SMASK, false).total), Bm((size_t)p_.Bm), c((int)(threadIdx.x >> 5) == NODE_WARP ? 0 : 1 + (int)(threadIdx.x & 31) % MT),
-          act(node_of(threadIdx.x) <= NT && ((int)(threadIdx.x >> 5) == NODE_WARP || (int)(threadIdx.x & 31) < NPW * MT)),
-          k(node_of(threadIdx.x) <= NT ? node_of(threadIdx.x) : NT)
+          warp(__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0)), sm(sm_), gm(gm_), o(MT, SMASK, false),
+          PHI(WOff(MT, SMASK, false).total), Bm((size_t)p_.Bm), c((int)(threadIdx.x >> 5) == NODE_WARP ? 0 : 1 + (int)(threadIdx.x & 31) % MT)
     {
+        obst_round(0);
         nc = 0;
         for (int kk = 0; kk <= N; kk++) nc += 2 * ((kk < N ? 2 : 0) + ((kk > 0 && kk < N) ? 4 : 0)) + 4 * M;
     }
 
-    __device__ __forceinline__ static int node_of(unsigned t)
+    // the (node, obstacle) pair of an obstacle thread in round r (node-warp threads: their node, whatever the round)
+    __device__ __forceinline__ void obst_round(int r)
     {
-        return (int)(t >> 5) == NODE_WARP ? (int)(t & 31) : (int)(t >> 5) * NPW + (int)(t & 31) / MT;
+        const int kn = warp == NODE_WARP ? lane : (r * NOW + warp) * NPW + lane / MT;
+        act = kn <= NT && (warp == NODE_WARP || lane < NPW * MT);
+        k = kn <= NT ? kn : NT;
     }
     __device__ __forceinline__ double& S(int row, int kk) const { return sm[row * NS + kk]; }
+    // row i of node-private field F at this thread's node: shared memory or the CTA's block of global memory
     template <int F>
-    __device__ __forceinline__ double& Q(int i) const { return sm[(o.pf[F] + i) * NS + k]; }
+    __device__ __forceinline__ double& Q(int i) const
+    {
+        if ((SMASK >> F) & 1u) return sm[(o.pf[F] + i) * NS + k];
+        return gm[(size_t)((o.pf[F] + i) * GS + k)];
+    }
+    // fields that other lanes read (v, pi, the steps, the refinement correction, the cost-to-go gradient) stay in shared memory
+    static_assert(((SMASK >> PF_V) & 1u) && ((SMASK >> PF_PI) & 1u) && ((SMASK >> PF_DV) & 1u) && ((SMASK >> PF_DPI) & 1u) &&
+                  ((SMASK >> PF_CPI) & 1u) && ((SMASK >> PF_PV) & 1u), "CTA kernel: v, pi, dv, dpi, cpi, pv live in shared memory");
     template <int F>
     __device__ __forceinline__ double& R(int i, int kk) const { return sm[(o.pf[F] + i) * NS + kk]; }
     __device__ __forceinline__ double& VV(int i, int kk) const { return sm[(o.pf[PF_V] + i) * NS + kk]; }
     __device__ __forceinline__ double& PP(int i, int kk) const { return sm[(o.pf[PF_PI] + i) * NS + kk]; }
+    // start of the rows of private field F (zero fill), its row stride, and its length
+    template <int F>
+    __device__ __forceinline__ double* field_base() const { return ((SMASK >> F) & 1u) ? sm + o.pf[F] * NS : gm + (size_t)o.pf[F] * GS; }
+    template <int F>
+    __device__ __forceinline__ static constexpr int field_stride() { return ((SMASK >> F) & 1u) ? NS : GS; }
     __device__ __forceinline__ bool box_on(int s, int kk) const { return s < 2 ? (kk < N) : (kk > 0 && kk < N); }
     __device__ __forceinline__ double scal(int kk) const { return kk < N ? p.dt : 1.0; }
     __device__ __forceinline__ void box_bounds(int s, double& lb, double& ub) const
@@ -145,8 +166,8 @@ struct CtaSolver {
     __device__ void prepare_and_init()
     {
         // rows that start at zero: lam, t, 1/t, dlam of every constraint slot, the step rows
-        for (int e = tid; e < nct * NS; e += NTHR) {
-            sm[o.pf[PF_LAM] * NS + e] = 0.0; sm[o.pf[PF_T] * NS + e] = 0.0; sm[o.pf[PF_TINV] * NS + e] = 0.0; sm[o.pf[PF_DD] * NS + e] = 0.0;
+        for (int e = tid; e < nct * field_stride<PF_LAM>(); e += NTHR) {
+            field_base<PF_LAM>()[e] = 0.0; field_base<PF_T>()[e] = 0.0; field_base<PF_TINV>()[e] = 0.0; field_base<PF_DD>()[e] = 0.0;
         }
         for (int e = tid; e < 7 * NS; e += NTHR) sm[o.pf[PF_DV] * NS + e] = 0.0;
         for (int e = tid; e < 5 * NS; e += NTHR) sm[o.pf[PF_DPI] * NS + e] = 0.0;
@@ -210,7 +231,10 @@ struct CtaSolver {
         }
         __syncthreads();
         // the obstacle threads need the linearisation point and the (possibly shifted) initial v of their node
-        if (!node_warp() && is_obst()) {
+        if (!node_warp())
+        for (int r_ = 0; r_ < OROUNDS; r_++) {
+            obst_round(r_);
+            if (!is_obst()) continue;
             const int j = c - 1;
             const double sc = scal(k);
             double xk[5] = {Q<PF_XU>(2), Q<PF_XU>(3), 0.0, 0.0, 0.0};
@@ -310,8 +334,13 @@ struct CtaSolver {
                 slot_add(gt, s, fma(-fma(lu_, rdu, mu_), tiu, fma(ll, rdl, ml) * til));
             }
         }
+        if (!node_warp())
+        for (int r_ = 0; r_ < OROUNDS; r_++) {
+        obst_round(r_);
+        const double sc = scal(k);
+        const double Zuq = sc * p.Zu;
         double o_rg2 = 0.0, o_rg3 = 0.0, o_h2 = 0.0, o_h3 = 0.0, o_hxy = 0.0, o_gt2 = 0.0, o_gt3 = 0.0;
-        if (!node_warp() && is_obst()) {
+        if (is_obst()) {
             const int j = c - 1;
             const double v2 = VV(2, k), v3 = VV(3, k);
             const double vo2 = S(o.cv + 2, k), vo3 = S(o.cv + 3, k), dv2 = R<PF_DV>(2, k), dv3 = R<PF_DV>(3, k);
@@ -348,15 +377,15 @@ struct CtaSolver {
             const double Zlq = Q<PF_ZZLQ>(j);
             const double rgsl = fma(Zlq, s_l, Q<PF_ZLQ>(j)) - l0 - l2;
             const double rgsu = fma(Zuq, s_u, sc * fma(p.Zu, sui, p.zu)) - l1 - l3;
-            n0 = fmax(fabs(rgsl), fabs(rgsu));
+            n0 = fmax(n0, fmax(fabs(rgsl), fabs(rgsu)));
             const double rd0 = cv + s_l - lgj - t0;
             const double rd1 = ugj - cv + s_u - t1;
             const double rd2 = s_l + sli - t2;
             const double rd3 = s_u + sui - t3;
-            n2 = fmax(fmax(fabs(rd0), fabs(rd1)), fmax(fabs(rd2), fabs(rd3)));
+            n2 = fmax(n2, fmax(fmax(fabs(rd0), fabs(rd1)), fmax(fabs(rd2), fabs(rd3))));
             const double m0 = l0 * t0, m1 = l1 * t1, m2 = l2 * t2, m3 = l3 * t3;
-            n3 = fmax(fmax(fabs(m0), fabs(m1)), fmax(fabs(m2), fabs(m3)));
-            sum = (m0 + m1) + (m2 + m3);
+            n3 = fmax(n3, fmax(fmax(fabs(m0), fabs(m1)), fmax(fabs(m2), fabs(m3))));
+            sum += (m0 + m1) + (m2 + m3);
             const double p01 = t0 * t1, p23 = t2 * t3;
             const double r4 = 1.0 / (p01 * p23);
             const double r01 = r4 * p23, r23 = r4 * p01;
@@ -377,13 +406,13 @@ struct CtaSolver {
             const double coef = fma(-(Gl * rhol), Dli, q0) - fma(-(Gu * rhou), Dui, q1);
             o_gt2 = cx * coef; o_gt3 = cy * coef;
         }
-        if (!node_warp()) {
-            o_rg2 = seg_sum(o_rg2); o_rg3 = seg_sum(o_rg3); o_h2 = seg_sum(o_h2); o_h3 = seg_sum(o_h3);
-            o_hxy = seg_sum(o_hxy); o_gt2 = seg_sum(o_gt2); o_gt3 = seg_sum(o_gt3);
-            if (is_obst() && c == 1) {
-                XCH(0) = o_rg2; XCH(1) = o_rg3; XCH(2) = o_h2; XCH(3) = o_h3; XCH(4) = o_hxy; XCH(5) = o_gt2; XCH(6) = o_gt3;
-            }
+        o_rg2 = seg_sum(o_rg2); o_rg3 = seg_sum(o_rg3); o_h2 = seg_sum(o_h2); o_h3 = seg_sum(o_h3);
+        o_hxy = seg_sum(o_hxy); o_gt2 = seg_sum(o_gt2); o_gt3 = seg_sum(o_gt3);
+        if (is_obst() && c == 1) {
+            XCH(0) = o_rg2; XCH(1) = o_rg3; XCH(2) = o_h2; XCH(3) = o_h3; XCH(4) = o_hxy; XCH(5) = o_gt2; XCH(6) = o_gt3;
         }
+        }
+        obst_round(0);
         __syncthreads();
         if (node_warp() && is_lead()) {
             rg[2] += XCH(0); rg[3] += XCH(1); Hx[2] += XCH(2); Hx[3] += XCH(3); hxy = XCH(4); gt[2] += XCH(5); gt[3] += XCH(6);
@@ -534,6 +563,10 @@ struct CtaSolver {
         const double Zuq = sc * p.Zu;
         double gt[7] = {0, 0, 0, 0, 0, 0, 0};
         if (!node_warp()) {
+            for (int r_ = 0; r_ < OROUNDS; r_++) {
+            obst_round(r_);
+            const double sc = scal(k);
+            const double Zuq = sc * p.Zu;
             double o2 = 0.0, o3 = 0.0;
             if (is_obst()) {
                 const int j = c - 1;
@@ -550,6 +583,8 @@ struct CtaSolver {
             }
             o2 = seg_sum(o2); o3 = seg_sum(o3);
             if (is_obst() && c == 1) { XCH(0) = o2; XCH(1) = o3; }
+            }
+            obst_round(0);
         } else if (is_lead() && kind != 3) {
             double v[7];
 #pragma unroll
@@ -770,12 +805,10 @@ struct CtaSolver {
     // expansion of the step of this thread's chunk (see mpc_wpp.cuh expand()): MODE XP_SOLVE (base solve `kind`),
     // XP_REFINE (add the refinement correction), XP_LIN (residual of the linear system; lrg2/lrg3: obstacle parts)
     template <int MODE>
-    __device__ __forceinline__ void expand(int kind, double& s1, double& s2, double* lrg, double& o2, double& o3, double& ln0)
+    __device__ __forceinline__ void expand_box(int kind, double& s1, double& s2, double* lrg)
     {
-        const double sc = scal(k);
-        const double Zuq = sc * p.Zu;
         const bool keep_dd = (MODE == XP_SOLVE) && kind == 0 && p.pred_corr;
-        if (node_warp() && is_lead()) {
+        if (is_lead()) {
             double v[7], dv[7], cv[7];
 #pragma unroll
             for (int i = 0; i < 7; i++) { v[i] = VV(i, k); dv[i] = R<PF_DV>(i, k); cv[i] = MODE == XP_REFINE ? S(o.cv + i, k) : 0.0; }
@@ -807,7 +840,15 @@ struct CtaSolver {
                 if (MODE == XP_LIN) slot_add(lrg, s, -dll + dlu);
             }
         }
-        if (!node_warp() && is_obst()) {
+    }
+    // ... and of the (node, obstacle) pair of an obstacle thread in the current round
+    template <int MODE>
+    __device__ __forceinline__ void expand_obst(int kind, double& s1, double& s2, double& o2, double& o3, double& ln0)
+    {
+        const double sc = scal(k);
+        const double Zuq = sc * p.Zu;
+        const bool keep_dd = (MODE == XP_SOLVE) && kind == 0 && p.pred_corr;
+        if (is_obst()) {
             const int j = c - 1;
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
             const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
@@ -865,7 +906,7 @@ struct CtaSolver {
                 const double a0 = fma(Q<PF_ZZLQ>(j), dsl, rgsl) - dl0 - dl2;
                 const double a1 = fma(Zuq, dsu, rgsu) - dl1 - dl3;
                 Q<PF_LRGSL>(j) = a0; Q<PF_LRGSU>(j) = a1;
-                ln0 = fmax(fabs(a0), fabs(a1));
+                ln0 = fmax(ln0, fmax(fabs(a0), fabs(a1)));
             }
         }
     }
@@ -901,8 +942,17 @@ struct CtaSolver {
         }
         double s1 = 0.0, s2 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0;
         ad_n = 1.0; ad_d = -1.0; ap_n = 1.0; ap_d = -1.0;
-        if (kind == 3) expand<XP_REFINE>(3, s1, s2, nullptr, d0, d1, d2);
-        else expand<XP_SOLVE>(kind, s1, s2, nullptr, d0, d1, d2);
+        if (node_warp()) {
+            if (kind == 3) expand_box<XP_REFINE>(3, s1, s2, nullptr);
+            else expand_box<XP_SOLVE>(kind, s1, s2, nullptr);
+        } else {
+            for (int r_ = 0; r_ < OROUNDS; r_++) {
+                obst_round(r_);
+                if (kind == 3) expand_obst<XP_REFINE>(3, s1, s2, d0, d1, d2);
+                else expand_obst<XP_SOLVE>(kind, s1, s2, d0, d1, d2);
+            }
+            obst_round(0);
+        }
         // negative-reciprocal convention (HPIPM d_compute_alpha_qp): the largest of the negative ratios limits the step
         double red[4] = {s1, s2, ap_n / ap_d, ad_n / ad_d};
         cta_reduce<2, 0, 2>(red);
@@ -938,10 +988,16 @@ struct CtaSolver {
                 for (int i = 0; i < 5; i++) lrg[2 + i] -= R<PF_DPI>(i, k - 1);
             }
         }
-        expand<XP_LIN>(0, s1, s2, lrg, o2, o3, ln0);
-        if (!node_warp()) {
-            o2 = seg_sum(o2); o3 = seg_sum(o3);
-            if (is_obst() && c == 1) { XCH(0) = o2; XCH(1) = o3; }
+        if (node_warp()) expand_box<XP_LIN>(0, s1, s2, lrg);
+        else {
+            for (int r_ = 0; r_ < OROUNDS; r_++) {
+                obst_round(r_);
+                o2 = 0.0; o3 = 0.0;
+                expand_obst<XP_LIN>(0, s1, s2, o2, o3, ln0);
+                o2 = seg_sum(o2); o3 = seg_sum(o3);
+                if (is_obst() && c == 1) { XCH(0) = o2; XCH(1) = o3; }
+            }
+            obst_round(0);
         }
         __syncthreads();
         if (node_warp() && is_lead()) {
@@ -1051,7 +1107,10 @@ struct CtaSolver {
                     p.T[((size_t)k * nct + o_lb + s) * Bm + b] = Q<PF_T>(o_lb + s); p.T[((size_t)k * nct + o_ub + s) * Bm + b] = Q<PF_T>(o_ub + s);
                 }
             }
-            if (!node_warp() && is_obst()) {
+            if (!node_warp())
+            for (int r_ = 0; r_ < OROUNDS; r_++) {
+                obst_round(r_);
+                if (!is_obst()) continue;
                 const int j = c - 1;
                 p.SL[((size_t)k * M + j) * Bm + b] += Q<PF_SL>(j);
                 p.SU[((size_t)k * M + j) * Bm + b] += Q<PF_SU>(j);
@@ -1090,17 +1149,22 @@ struct CtaSolver {
 #define B2_CTA_MINB 2           // resident CTAs per SM the kernel is compiled for: 168 registers.  (61 KB of shared memory per problem
                                 // would allow 3 at 128 registers: measured 6.5 % slower per problem, 1.426 vs 1.333 ms)
 #endif
-// dynamic shared memory of the CTA kernel: the all-shared layout of mpc_wpp.cuh + the Phi rows
-__host__ __device__ inline size_t b2_cta_smem_bytes(int N, int M)
+// dynamic shared memory of the CTA kernel: the shared rows of the chosen placement (mpc_wpp.cuh WOff) + the Phi rows + scratch
+__host__ __device__ inline size_t b2_cta_smem_bytes(int N, int M, unsigned long long smask = B2_WPP_ALL_SHARED)
 {
-    return b2_wpp_smem_bytes(N, M, B2_WPP_ALL_SHARED) + sizeof(double) * B2_CTA_PHI_ROWS * (size_t)b2_wpp_stride(N);
+    return sizeof(double) * ((size_t)(WOff(M, smask, false).total + B2_CTA_PHI_ROWS) * b2_wpp_stride(N) + B2_WPP_SCRATCH);
 }
 
-template <int MT, int NT>
-__global__ void __launch_bounds__(CtaSolver<MT, NT>::NTHR, B2_CTA_MINB) b2_rti_solve_cta(const B2Params p)
+// MINB: resident CTAs per SM the instantiation is compiled for (register budget 65536 / (MINB * threads)).
+//   latency kernel  <5, N, 0, ALL_SHARED, 2>: 168 registers (61 KB of shared memory per problem would allow 3 CTAs at 128
+//                                             registers: measured 6.5 % slower per problem, 1.426 vs 1.333 ms)
+//   throughput candidates <5, 20, 1 or 2, ALL_GLOBAL, 8 or 6>: node-private rows in L2 like the warp kernel, 22 KB of shared memory
+template <int MT, int NT, int NOW_ = 0, unsigned long long SMASK_ = B2_WPP_ALL_SHARED, int MINB = 2>
+__global__ void __launch_bounds__(CtaSolver<MT, NT, NOW_, SMASK_>::NTHR, MINB) b2_rti_solve_cta(const B2Params p)
 {
     B2_DYNAMIC_SMEM(double, b2_smem);
     __shared__ int s_next;
+    double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows (if any)
     const int nq = p.NQ ? *p.NQ : p.B;
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(p.NEXT, 1);
@@ -1109,7 +1173,7 @@ __global__ void __launch_bounds__(CtaSolver<MT, NT>::NTHR, B2_CTA_MINB) b2_rti_s
         __syncthreads();
         if (i >= nq) break;
         const int b = p.ORDER ? p.ORDER[i] : i;
-        CtaSolver<MT, NT> s(p, b, b2_smem);
+        CtaSolver<MT, NT, NOW_, SMASK_> s(p, b, b2_smem, gm);
         s.run();
     }
 }
