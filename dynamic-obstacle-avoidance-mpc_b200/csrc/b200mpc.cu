@@ -228,6 +228,7 @@ extern "C" int b2mpc_create(const b2mpc_config* cfg, b2mpc** out)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->wpp_fn, 32, h->wpp_smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         if (occ < 1) { b2mpc_destroy(h); return fail(B2MPC_ECUDA, "warp kernel does not fit an SM"); }
+        if (const char* e = getenv("B2MPC_WPP_OCC")) { if (atoi(e) > 0 && atoi(e) < occ) occ = atoi(e); }   // experiment: fewer resident CTAs per SM
         h->wpp_grid = occ * sms;
         if (h->wpp_grid > h->Bm) h->wpp_grid = h->Bm;
         h->prm.wpriv_stride = b2_wpp_priv_doubles(N, M, smask);              // RTI launches keep their compact blocks (L2 footprint)

@@ -21,7 +21,18 @@
 #pragma once
 #include "mpc_wpp.cuh"
 
-#define B2_CTA_PHI_ROWS 25       // rows appended to the all-shared layout of mpc_wpp.cuh: the entries of Phi_k (feedback form)
+// B2_CTA_SCAN: the two vector recursions of a KKT solve (p_k = c'_k + Phi_k^T p_{k+1}, dx_{k+1} = f_k + Phi_k dx_k) as PARALLEL
+// SCANS over the nodes (Hillis-Steele, ceil(log2 N) levels of one 5 x 5 matrix-vector product per node) instead of N sequential
+// steps: the products G(d)_j = Phi_{j-1} Phi_{j-2} ... Phi_{j-2^d} are formed once per factorisation by all threads of the CTA
+// (both directions use them: the backward operator of level d at node k is G(d)_{k+2^d} transposed).  More arithmetic, a
+// dependent chain of 5 levels instead of 19 nodes: this is the latency kernel.  (The same idea LOST as a throughput kernel,
+// profiles/experiments/r01_scan_variant.md: there the instruction count is what matters.)  0 restores the sequential sweeps.
+#ifndef B2_CTA_SCAN
+#define B2_CTA_SCAN 1
+#endif
+#define B2_CTA_SCAN_LEVELS 4     // stored product levels G(1) .. G(4): horizons up to 32 nodes
+// rows appended to the all-shared layout of mpc_wpp.cuh: the entries of Phi_k (feedback form) + the scan products
+#define B2_CTA_PHI_ROWS (25 + (B2_CTA_SCAN ? 25 * B2_CTA_SCAN_LEVELS : 0))
 
 // NOW_: obstacle warps per problem (0 = one (node, obstacle) pair per thread: ceil((N+1) / (32/M)) warps, the latency
 // configuration; fewer warps walk the pairs in rounds).  SMASK_: placement of the node-private fields as in mpc_wpp.cuh
@@ -47,6 +58,8 @@ struct CtaSolver {
     double* const gm;       // this CTA's block of node-private rows in global memory (fields whose SMASK bit is clear)
     const WOff o;
     const int PHI;          // first of the 25 rows of Phi
+    const int GSC;          // first row of the scan products G(1), G(2), ... (25 rows each)
+    static constexpr int LV = NT > 16 ? 5 : NT > 8 ? 4 : NT > 4 ? 3 : NT > 2 ? 2 : 1;      // scan levels: 2^LV >= N
     const size_t Bm;
     const int c;            // obstacle warps: 1 + obstacle index of this thread; node warp: 0
     bool act;               // the thread owns a node (node warp) or, in the current round, a (node, obstacle) pair (obstacle warps)
@@ -57,6 +70,7 @@ struct CtaSolver {
     double ad_n, ad_d, ap_n, ap_d;
 #ifdef B2_DEBUG_CLOCK
     long long clk_fact = 0, clk_sweep = 0, clk_all = 0, clk_head = 0, clk_prep = 0, clk_rs = 0, clk_exp = 0, clk_lin = 0;
+    long long clk_fa = 0, clk_fb = 0, clk_fc = 0, clk_fe = 0;       // -DB2_DEBUG_CLOCK_FACT: phases of the factorisation
 #endif
 
     __device__ CtaSolver(const B2Params& p_, int b_, double* sm_, double* gm_)
@@ -65,7 +79,7 @@ struct CtaSolver {
           // sweeps is a uniform branch and the shuffles inside are compiled for a converged warp (without it every shuffle
           // of the factorisation went through the divergent-warp path: WARPSYNC.COLLECTIVE per SHFL, 7x slower sweeps)
           warp(__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0)), sm(sm_), gm(gm_), o(MT, SMASK, false),
-          PHI(WOff(MT, SMASK, false).total), Bm((size_t)p_.Bm), c((int)(threadIdx.x >> 5) == NODE_WARP ? 0 : 1 + (int)(threadIdx.x & 31) % MT)
+          PHI(WOff(MT, SMASK, false).total), GSC(WOff(MT, SMASK, false).total + 25), Bm((size_t)p_.Bm), c((int)(threadIdx.x >> 5) == NODE_WARP ? 0 : 1 + (int)(threadIdx.x & 31) % MT)
     {
         obst_round(0);
         nc = 0;
@@ -464,6 +478,10 @@ struct CtaSolver {
         const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
         double* const scr = sm + (o.total + PHI_ROWS) * NS;
         for (int kk = N; kk >= 0; kk--) {
+#ifdef B2_DEBUG_CLOCK_FACT
+            const long long tf0_ = clock64();
+            long long tfa_ = tf0_;
+#endif
             double m = 0.0;
             if (mi == mj) m = S(o.cv + mi, kk);
             if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
@@ -487,11 +505,17 @@ struct CtaSolver {
                     }
                 }
                 __syncwarp();
+#ifdef B2_DEBUG_CLOCK_FACT
+                tfa_ = clock64();
+#endif
                 double acc = 0.0;
 #pragma unroll
                 for (int q = 0; q < 5; q++) acc = fma(scr[mi * 5 + q], scr[mj * 5 + q], acc);
                 m += acc;
             }
+#ifdef B2_DEBUG_CLOCK_FACT
+            const long long tfb_ = clock64() + (long long)(m == 1.2345e-300);
+#endif
             double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
             // (unrolled: one problem per CTA is latency-bound, the compile-time shuffle lanes save the index arithmetic of the
             //  rolled loop that the throughput kernel prefers for its instruction-cache footprint)
@@ -509,15 +533,19 @@ struct CtaSolver {
                 if (cc == 0) sp0 = sp;
                 if (mj == cc) my_sp = sp;
                 if (ok) {
-                    const int ex = ((__double2hiint(pv_) >> 20) & 0x7ff) - 1023;
-                    const double scale = __hiloint2double((1023 - ex) << 20, 0);
-                    const double pn = pv_ * scale;
-                    if (mj > cc) m = fma(m, pn, -((la * lb) * scale));
-                    sigma *= pn;
+                    // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
+                    // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
+                    // of two commutes with the rounding), one multiplication shorter on the dependent chain
+                    const double scale = __hiloint2double(0x7fe00000 - (__double2hiint(pv_) & 0x7ff00000), 0);
+                    if (mj > cc) m = fma(m, pv_, -(la * lb)) * scale;
+                    sigma *= pv_ * scale;
                 }
             }
             // 1/sqrt(x) = sqrt(x) * (1/x): the square root and the reciprocal run side by side (both correctly rounded
             // operations, like the mirror's), one multiplication after the slower of the two instead of a division after the root
+#ifdef B2_DEBUG_CLOCK_FACT
+            const long long tfc_ = clock64() + (long long)(m == 1.2345e-300);
+#endif
             const double myrs = my_sp > 0.0 ? sqrt(my_sp) * (1.0 / my_sp) : 0.0;
             m *= myrs;
             const double rs0 = b2_bcast(myrs, 0);
@@ -530,6 +558,10 @@ struct CtaSolver {
                 if (xu) S(lrow, kk) = m;
             }
             __syncwarp();
+#ifdef B2_DEBUG_CLOCK_FACT
+            const long long tfe_ = clock64();
+            clk_fa += tfa_ - tf0_; clk_fb += tfb_ - tfa_; clk_fc += tfc_ - tfb_; clk_fe += tfe_ - tfc_;
+#endif
         }
     }
 
@@ -671,6 +703,40 @@ struct CtaSolver {
         }
     }
 
+    // entry (r, q) of G(d)_j, d >= 0:  G(0)_j = Phi_{j-1},  G(d)_j = Phi_{j-1} ... Phi_{j-2^d}  (defined for j - 2^d >= 1)
+    __device__ __forceinline__ double& GD(int d, int r, int q, int j) const
+    {
+        return d == 0 ? S(PHI + r * 5 + q, j - 1) : S(GSC + (d - 1) * 25 + r * 5 + q, j);
+    }
+    // G(d+1)_j = G(d)_j G(d)_{j-2^d} for every node j >= 2^(d+1) + 1, one thread per (node, row); all threads of the CTA, once per
+    // factorisation (block barriers inside: every thread of the CTA must call it)
+    __device__ void scan_products()
+    {
+#if B2_CTA_SCAN
+#pragma unroll 1
+        for (int d = 0; d + 1 < LV; d++) {
+            const int s_ = 1 << d;
+            for (int e = tid; e < 5 * (N + 1); e += NTHR) {
+                const int j = e / 5, r = e - 5 * j;
+                if (j < 2 * s_ + 1 || j > N) continue;
+                double a[5], acc[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) a[q] = GD(d, r, q, j);
+#pragma unroll
+                for (int cq = 0; cq < 5; cq++) {
+                    double t = a[0] * GD(d, 0, cq, j - s_);
+#pragma unroll
+                    for (int q = 1; q < 5; q++) t = fma(a[q], GD(d, q, cq, j - s_), t);
+                    acc[cq] = t;
+                }
+#pragma unroll
+                for (int cq = 0; cq < 5; cq++) GD(d + 1, r, cq, j) = acc[cq];
+            }
+            __syncthreads();
+        }
+#endif
+    }
+
     // (Experiment, negative: every lane carrying the whole 5-vector with all 25 entries of Phi as broadcast loads -- no shuffle
     //  on the chain -- measured 2.1x SLOWER sweeps (38.6 k vs 18.3 k cycles per iteration): 25 FP64 operations per node and
     //  lane on a half-rate pipe cost more than the 26-cycle broadcast they avoid.)
@@ -707,6 +773,37 @@ struct CtaSolver {
             const long long c1_ = clock64();
 #endif
             // ---- backward: p_k = c'_k + Phi_k^T p_{k+1}
+#if B2_CTA_SCAN
+            // suffix scan, lane = node k: after level d the row holds p_k up to the influence of p_{k+2^(d+1)}; node N (p_N given,
+            // no operator) ends every chain.  Branch-free: every lane computes (indices clamped), the lanes of the level store.
+            if (is_lead() && k >= 1) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) R<PF_PV>(i, k) = S(o.hg + 2 + i, k);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < LV; d++) {
+                const int s_ = 1 << d;
+                const bool on = is_lead() && k >= 1 && k + s_ <= N;
+                const int kn = k + s_ <= N ? k + s_ : N, kc = k >= 1 ? k : 1;
+                double cn[5], acc[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) cn[q] = R<PF_PV>(q, kn);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    double t = R<PF_PV>(i, kc);
+#pragma unroll
+                    for (int q = 0; q < 5; q++) t = fma(GD(d, q, i, kn), cn[q], t);
+                    acc[i] = t;
+                }
+                __syncwarp();
+                if (on) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) R<PF_PV>(i, k) = acc[i];
+                }
+                __syncwarp();
+            }
+#else
             const int c5 = lane < 5 ? lane : 4;
             double pf[5];
             {
@@ -723,6 +820,7 @@ struct CtaSolver {
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
             }
+#endif
 #ifdef B2_DEBUG_CLOCK
             clk_sweep += clock64() - c1_;
 #endif
@@ -754,6 +852,31 @@ struct CtaSolver {
             const long long c2_ = clock64();
 #endif
             // ---- forward: dx_{k+1} = f_k + Phi_k dx_k  (dx_1 = f_0)
+#if B2_CTA_SCAN
+            // prefix scan, lane = node j: the row dv[2..6](j) holds f_{j-1} on entry (written by the mid phase) and dx_j on exit
+#pragma unroll
+            for (int d = 0; d < LV; d++) {
+                const int s_ = 1 << d;
+                const bool on = is_lead() && k - s_ >= 1;
+                const int kc = k >= s_ + 1 ? k : s_ + 1;        // (clamped: G(d)_j exists for j >= 2^d + 1)
+                double yn[5], acc[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) yn[q] = S(oDV + 2 + q, kc - s_);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    double t = S(oDV + 2 + i, kc);
+#pragma unroll
+                    for (int q = 0; q < 5; q++) t = fma(GD(d, i, q, kc), yn[q], t);
+                    acc[i] = t;
+                }
+                __syncwarp();
+                if (on) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) S(oDV + 2 + i, k) = acc[i];
+                }
+                __syncwarp();
+            }
+#else
             double dx[5];
             {
                 const double xn = S(oDV + 2 + c5, 1);
@@ -768,6 +891,7 @@ struct CtaSolver {
 #pragma unroll
                 for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
             }
+#endif
 #ifdef B2_DEBUG_CLOCK
             clk_sweep += clock64() - c2_;
 #endif
@@ -1049,10 +1173,11 @@ struct CtaSolver {
             const long long c0_ = clock64();
 #endif
             if (node_warp()) { riccati_factorize(); feedback_matrices(); }
+            __syncthreads();
+            scan_products();
 #ifdef B2_DEBUG_CLOCK
             clk_fact += clock64() - c0_;
 #endif
-            __syncthreads();
             int kind = 0, itref = 0;
             double smu = 0.0, mu_aff0 = 0.0;
             for (;;) {
@@ -1128,6 +1253,9 @@ struct CtaSolver {
             p.STATS[5 * Bm + b] = (double)clk_fact; p.STATS[6 * Bm + b] = (double)clk_sweep; p.STATS[7 * Bm + b] = (double)clk_all;
             p.STATS[0 * Bm + b] = (double)clk_head; p.STATS[1 * Bm + b] = (double)clk_prep; p.STATS[2 * Bm + b] = (double)clk_rs;
             p.STATS[3 * Bm + b] = (double)clk_exp; p.STATS[4 * Bm + b] = (double)clk_lin;
+#ifdef B2_DEBUG_CLOCK_FACT
+            p.STATS[0 * Bm + b] = (double)clk_fa; p.STATS[1 * Bm + b] = (double)clk_fb; p.STATS[2 * Bm + b] = (double)clk_fc; p.STATS[3 * Bm + b] = (double)clk_fe;
+#endif
         }
         if (tid != 0 || true) {}
 #endif

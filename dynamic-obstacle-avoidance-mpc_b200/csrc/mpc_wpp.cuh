@@ -76,6 +76,36 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 #ifndef B2_WPP_MINB
 #define B2_WPP_MINB 12          // resident CTAs per SM the N=20 layout is compiled for (register cap 65536/32/MINB = 170)
 #endif
+// Software prefetch of the node-private rows that live in global memory.  With one warp per problem a node-parallel pass is a
+// chain of round trips: the loads of one box slot / obstacle are issued back to back, the warp sleeps until they return, the
+// next obstacle follows.  At N = 100, M = 20 the private rows of the resident problems (592 x 0.68 MB) are 3x the L2, so every
+// one of the ~600 round trips of an interior-point iteration goes to DRAM (measured: 1.6 M cycles per iteration = 600 x 2.7 k).
+// `prefetch.global.L2` of the rows of obstacle j + PFD (and of the next node round) costs no registers and turns those
+// round trips into L2 hits.
+//   B2_WPP_PF_LONG : cache level for horizons > 32 nodes (0 off, 2 = L2, 1 = L1), B2_WPP_PF_SHORT: the same for N <= 32
+//   B2_WPP_PFD     : prefetch distance in obstacles
+#ifndef B2_WPP_PF_LONG
+#define B2_WPP_PF_LONG 2
+#endif
+#ifndef B2_WPP_PF_SHORT
+#define B2_WPP_PF_SHORT 0
+#endif
+#ifndef B2_WPP_PFD
+#define B2_WPP_PFD 1
+#endif
+#ifndef B2_WPP_PF_NODE
+#define B2_WPP_PF_NODE 0          // also prefetch the node-level rows / box slots of the next node round
+#endif
+template <int LEVEL>
+__device__ __forceinline__ void b2_prefetch(const void* ptr)
+{
+#ifndef SIMT_EMU
+    if (LEVEL == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    if (LEVEL == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
 
 struct WOff {
     int sv, hg, rb, lrb, cv, lamu, lxu, lxx, lu;                               // shared-memory rows read across lanes
@@ -218,6 +248,84 @@ struct WppSolver {
     {
         const double xv = Q<PF_XU>(s);
         lb = p.lb6[s] - xv; ub = p.ub6[s] - xv;          // [lbu, lbx] / [ubu, ubx] in slot order
+    }
+
+    // ---- software prefetch of private rows (see B2_WPP_PF_LONG above) ---------------------------------------------
+    static constexpr int PFL = (NT > 32) ? B2_WPP_PF_LONG : (NT > 0 ? B2_WPP_PF_SHORT : 0);      // cache level, 0 = off
+    static constexpr int PFD = B2_WPP_PFD;
+#define B2_FM(f) (1ull << (f))
+    // fields READ per obstacle / per node by each pass (write-only rows need no fetch: full sectors are written)
+    static constexpr unsigned long long FM_OBST_IN = B2_FM(PF_CX) | B2_FM(PF_CY) | B2_FM(PF_LG) | B2_FM(PF_UG) | B2_FM(PF_SLI) |
+                                                     B2_FM(PF_SUI) | B2_FM(PF_SL) | B2_FM(PF_SU);
+    static constexpr unsigned long long FM_HEAD = FM_OBST_IN | B2_FM(PF_LAM) | B2_FM(PF_T) | B2_FM(PF_DD) | B2_FM(PF_DSL) | B2_FM(PF_DSU) |
+                                                  B2_FM(PF_ZLQ) | B2_FM(PF_ZZLQ) | B2_FM(PF_G) | B2_FM(PF_XU) | B2_FM(PF_V) | B2_FM(PF_PI) |
+                                                  B2_FM(PF_DV) | B2_FM(PF_B);
+    static constexpr unsigned long long FM_SOLVE = FM_OBST_IN | B2_FM(PF_LAM) | B2_FM(PF_T) | B2_FM(PF_TINV) | B2_FM(PF_DD) | B2_FM(PF_ZLQ) |
+                                                   B2_FM(PF_ZZLQ) | B2_FM(PF_DLI) | B2_FM(PF_DUI) | B2_FM(PF_XU) | B2_FM(PF_V) | B2_FM(PF_DV);
+    static constexpr unsigned long long FM_PREP = FM_SOLVE | B2_FM(PF_RG);
+    static constexpr unsigned long long FM_PREP3 = B2_FM(PF_LAM) | B2_FM(PF_TINV) | B2_FM(PF_LRGSL) | B2_FM(PF_LRGSU) | B2_FM(PF_DLI) |
+                                                   B2_FM(PF_DUI) | B2_FM(PF_CX) | B2_FM(PF_CY);
+    static constexpr unsigned long long FM_REFINE = FM_OBST_IN | B2_FM(PF_LAM) | B2_FM(PF_T) | B2_FM(PF_TINV) | B2_FM(PF_DD) | B2_FM(PF_LRGSL) |
+                                                    B2_FM(PF_LRGSU) | B2_FM(PF_DLI) | B2_FM(PF_DUI) | B2_FM(PF_DSL) | B2_FM(PF_DSU) | B2_FM(PF_XU) |
+                                                    B2_FM(PF_V) | B2_FM(PF_DV) | B2_FM(PF_DPI) | B2_FM(PF_CPI);
+    static constexpr unsigned long long FM_LIN = FM_OBST_IN | B2_FM(PF_LAM) | B2_FM(PF_T) | B2_FM(PF_DD) | B2_FM(PF_DSL) | B2_FM(PF_DSU) |
+                                                 B2_FM(PF_ZLQ) | B2_FM(PF_ZZLQ) | B2_FM(PF_XU) | B2_FM(PF_DV) | B2_FM(PF_RG) | B2_FM(PF_DPI);
+    template <int F>
+    __device__ __forceinline__ void pfq(int i, int kk) const
+    {
+        if (!((SMASK >> F) & 1u)) b2_prefetch<PFL>(gm + (size_t)((o.pf[F] + i) * GS + kk));
+    }
+    template <int F, unsigned long long FM>
+    __device__ __forceinline__ void pf_con4(int j, int kk) const       // the four constraint rows of obstacle j
+    {
+        if ((FM >> F) & 1u) { pfq<F>(o_lg + j, kk); pfq<F>(o_ug + j, kk); pfq<F>(o_ls + j, kk); pfq<F>(o_us + j, kk); }
+    }
+    template <int F, unsigned long long FM>
+    __device__ __forceinline__ void pf_one(int j, int kk) const
+    {
+        if ((FM >> F) & 1u) pfq<F>(j, kk);
+    }
+    template <int F, unsigned long long FM>
+    __device__ __forceinline__ void pf_rows(int i0, int n, int kk) const
+    {
+        if ((FM >> F) & 1u) {
+#pragma unroll
+            for (int i = 0; i < n; i++) pfq<F>(i0 + i, kk);
+        }
+    }
+    // rows of obstacle j at node kk that pass FM reads
+    template <unsigned long long FM>
+    __device__ __forceinline__ void prefetch_obst(int j, int kk) const
+    {
+        if (PFL == 0 || kk > N) return;
+        pf_con4<PF_LAM, FM>(j, kk); pf_con4<PF_T, FM>(j, kk); pf_con4<PF_TINV, FM>(j, kk); pf_con4<PF_DD, FM>(j, kk);
+        pf_one<PF_CX, FM>(j, kk); pf_one<PF_CY, FM>(j, kk); pf_one<PF_LG, FM>(j, kk); pf_one<PF_UG, FM>(j, kk);
+        pf_one<PF_ZLQ, FM>(j, kk); pf_one<PF_ZZLQ, FM>(j, kk); pf_one<PF_SLI, FM>(j, kk); pf_one<PF_SUI, FM>(j, kk);
+        pf_one<PF_SL, FM>(j, kk); pf_one<PF_SU, FM>(j, kk); pf_one<PF_LRGSL, FM>(j, kk); pf_one<PF_LRGSU, FM>(j, kk);
+        pf_one<PF_DSL, FM>(j, kk); pf_one<PF_DSU, FM>(j, kk); pf_one<PF_DLI, FM>(j, kk); pf_one<PF_DUI, FM>(j, kk);
+    }
+    // node-level rows and the six box slots of node kk that pass FM reads, plus its first PFD obstacles
+    template <unsigned long long FM>
+    __device__ __forceinline__ void prefetch_node(int kk) const
+    {
+        if (PFL == 0 || kk > N) return;
+        pf_rows<PF_LAM, FM>(o_lb, 6, kk); pf_rows<PF_LAM, FM>(o_ub, 6, kk);
+        pf_rows<PF_T, FM>(o_lb, 6, kk); pf_rows<PF_T, FM>(o_ub, 6, kk);
+        pf_rows<PF_TINV, FM>(o_lb, 6, kk); pf_rows<PF_TINV, FM>(o_ub, 6, kk);
+        pf_rows<PF_DD, FM>(o_lb, 6, kk); pf_rows<PF_DD, FM>(o_ub, 6, kk);
+        pf_rows<PF_B, FM>(0, 5, kk); pf_rows<PF_G, FM>(0, 7, kk); pf_rows<PF_RG, FM>(0, 7, kk); pf_rows<PF_XU, FM>(0, 6, kk);
+        pf_rows<PF_V, FM>(0, 7, kk); pf_rows<PF_PI, FM>(0, 5, kk); pf_rows<PF_DV, FM>(0, 7, kk); pf_rows<PF_DPI, FM>(0, 5, kk);
+        pf_rows<PF_CPI, FM>(0, 5, kk);
+        for (int j = 0; j < PFD && j < M; j++) prefetch_obst<FM>(j, kk);
+    }
+    // inside the obstacle loop of node k, before obstacle j is processed: obstacle j + PFD of this node, or -- past the last
+    // obstacle -- nothing (the first PFD obstacles of the next node round were prefetched with its node-level rows at j = 0)
+    template <unsigned long long FM>
+    __device__ __forceinline__ void prefetch_ahead(int j) const
+    {
+        if (PFL == 0) return;
+        if (B2_WPP_PF_NODE && j == 0) prefetch_node<FM>(k + 32);
+        if (j + PFD < M) prefetch_obst<FM>(j + PFD, k);
     }
 
     // ---- preparation + cold-start initialisation: lane k handles node k ----------------------------
@@ -421,6 +529,7 @@ struct WppSolver {
             if (B2_WPP_NO_DT) { vo2 = S(o.cv + 2, k); vo3 = S(o.cv + 3, k); dv2 = R<PF_DV>(2, k); dv3 = R<PF_DV>(3, k); }
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
+                prefetch_ahead<FM_HEAD>(j);
                 const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
                 double l0 = fma(a, Q<PF_DD>(i0), Q<PF_LAM>(i0)), l1 = fma(a, Q<PF_DD>(i1), Q<PF_LAM>(i1));
                 double l2 = fma(a, Q<PF_DD>(i2), Q<PF_LAM>(i2)), l3 = fma(a, Q<PF_DD>(i3), Q<PF_LAM>(i3));
@@ -592,11 +701,12 @@ struct WppSolver {
                 if (c == 0) sp0 = sp;
                 if (mj == c) my_sp = sp;
                 if (ok) {
-                    const int ex = ((__double2hiint(pv_) >> 20) & 0x7ff) - 1023;
-                    const double scale = __hiloint2double((1023 - ex) << 20, 0);
-                    const double pn = pv_ * scale;
-                    if (mj > c) m = fma(m, pn, -((la * lb) * scale));
-                    sigma *= pn;
+                    // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
+                    // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
+                    // of two commutes with the rounding), one multiplication shorter on the dependent chain
+                    const double scale = __hiloint2double(0x7fe00000 - (__double2hiint(pv_) & 0x7ff00000), 0);
+                    if (mj > c) m = fma(m, pv_, -(la * lb)) * scale;
+                    sigma *= pv_ * scale;
                 }
             }
             // one rsqrt per lane (its own column); 1/L00 and 1/L11 come from the diagonal lanes 0 and 2:
@@ -661,6 +771,7 @@ struct WppSolver {
                 for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, k);          // lin_residuals left lrg here
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
+                    prefetch_ahead<FM_PREP3>(j);
                     const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
                     const double coef = fma(G1 * Q<PF_LRGSU>(j), Q<PF_DUI>(j), -((G0 * Q<PF_LRGSL>(j)) * Q<PF_DLI>(j)));
                     gt[2] = fma(Q<PF_CX>(j), coef, gt[2]);
@@ -686,6 +797,7 @@ struct WppSolver {
                 const double Zuq = sc * p.Zu;
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
+                    prefetch_ahead<FM_PREP>(j);
                     double rhol, rhou, q0, q1;
                     slack_rho(kind, smu, j, v, Zuq, sc, rhol, rhou, q0, q1);
                     const double G0 = Q<PF_LAM>(o_lg + j) * Q<PF_TINV>(o_lg + j), G1 = Q<PF_LAM>(o_ug + j) * Q<PF_TINV>(o_ug + j);
@@ -900,6 +1012,7 @@ struct WppSolver {
         }
 #pragma unroll JU
         for (int j = 0; j < M; j++) {
+            prefetch_ahead<MODE == XP_SOLVE ? FM_SOLVE : MODE == XP_REFINE ? FM_REFINE : FM_LIN>(j);
             const int i0 = o_lg + j, i1 = o_ug + j, i2 = o_ls + j, i3 = o_us + j;
             const double cx = Q<PF_CX>(j), cy = Q<PF_CY>(j);
             const double cdv = fma(cy, dv[3], cx * dv[2]);
@@ -1364,6 +1477,14 @@ __global__ void B2_WPP_BOUNDS(NT, SMASK) b2_rti_solve_wpp(const B2Params p)
     B2_DYNAMIC_SMEM(double, b2_smem);
     double* const gm = p.WPRIV + (size_t)blockIdx.x * p.wpriv_stride;      // this CTA's block of node-private rows
     const int nq = p.NQ ? *p.NQ : p.B;
+#if defined(B2_WPP_STAGGER) && !defined(SIMT_EMU)
+    // experiment: the resident CTAs of an SM start B2_WPP_STAGGER cycles apart, so that the first wave of a launch does not walk
+    // through the phases of the interior-point iteration in lock-step (timing only, results unchanged)
+    {
+        const long long t0 = clock64(), d = (long long)((blockIdx.x / 148u) % 12u) * B2_WPP_STAGGER;
+        while (clock64() - t0 < d) __nanosleep(500);
+    }
+#endif
     for (;;) {
         int i = 0;
         if ((threadIdx.x & 31) == 0) i = atomicAdd(p.NEXT, 1);

@@ -4,7 +4,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, 'dynamic-obstacle-avoidance-mpc_b200'))
 import torch, numpy as np
 from b200mpc import BatchedMpcSolver, world, capi
-capi.LIB_PATH = os.path.join(R, 'dynamic-obstacle-avoidance-mpc_b200', 'lib', 'libb200mpc_dbg.so')
+capi.LIB_PATH = os.path.join(R, os.environ.get('B2MPC_LIB', 'dynamic-obstacle-avoidance-mpc_b200/lib/libb200mpc_dbg.so'))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 dims = world.MpcDims(N, 5, N / 10.0); sc = world.random_scenarios(B, dims, seed=0)
