@@ -468,14 +468,18 @@ struct CtaSolver {
         // the last row in a convergence group of their own for the whole factorisation (measured active mask 0xf01fffff)
         const int mi = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21);
         const int mj = e - mi * (mi + 1) / 2;
-        const int ai0 = lane / 5, aq0 = lane % 5, ai1 = (32 + lane) / 5, aq1 = (32 + lane) % 5;
+        // (structure and arithmetic of mpc_wpp.cuh riccati_factorize(): U = [B A]^T Sxx with the unnormalised factor, M = H + U D^2 U^T,
+        //  the normalisation of the factor after the recursion -- there by the warp, here by all threads: normalize_factor())
+        const int ai0 = lane < 30 ? lane / 5 : 0, aq0 = lane % 5;
         int ba0[5], ba1[5];
 #pragma unroll
-        for (int r = 0; r < 5; r++) { ba0[r] = o.sv + B2_BATAB[r][ai0]; ba1[r] = o.sv + B2_BATAB[r][ai1 < 7 ? ai1 : 0]; }
+        for (int r = 0; r < 5; r++) { ba0[r] = o.sv + B2_BATAB[r][ai0]; ba1[r] = o.sv + B2_BATAB[r][6]; }
         const bool xx = lane < 28 && mi >= 2 && mj >= 2;
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
         const int xrow = xx ? o.lxx + b2_sym(mi - 2, mj - 2) : 0;
         const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
+        const bool dg = lane < 28 && mi == mj;
+        const int sprow = mj == 0 ? o.lamu + 0 : mj == 1 ? o.lamu + 2 : o.lrb + (mj - 2);
         double* const scr = sm + (o.total + PHI_ROWS) * NS;
         for (int kk = N; kk >= 0; kk--) {
 #ifdef B2_DEBUG_CLOCK_FACT
@@ -487,21 +491,23 @@ struct CtaSolver {
             if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
             if (kk < N) {
                 {
+                    const double spq = S(o.lrb + aq0, kk + 1);
+                    const double dq = spq > 0.0 ? 1.0 / spq : 0.0;
                     double acc = 0.0;
 #pragma unroll
                     for (int r = 0; r < 5; r++) {
                         const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
                         acc = fma(S(ba0[r], kk), l, acc);
                     }
-                    scr[lane] = acc;
-                    if (lane < 3) {
+                    if (lane < 30) { scr[lane] = acc; scr[40 + lane] = acc * dq; }
+                    if (lane < 5) {
                         double acc1 = 0.0;
 #pragma unroll
                         for (int r = 0; r < 5; r++) {
-                            const double l = (r >= aq1) ? S(o.lxx + b2_sym(r, aq1 <= r ? aq1 : r), kk + 1) : 0.0;
+                            const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
                             acc1 = fma(S(ba1[r], kk), l, acc1);
                         }
-                        scr[32 + lane] = acc1;
+                        scr[30 + lane] = acc1; scr[70 + lane] = acc1 * dq;
                     }
                 }
                 __syncwarp();
@@ -510,13 +516,13 @@ struct CtaSolver {
 #endif
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 5; q++) acc = fma(scr[mi * 5 + q], scr[mj * 5 + q], acc);
+                for (int q = 0; q < 5; q++) acc = fma(scr[40 + mi * 5 + q], scr[mj * 5 + q], acc);
                 m += acc;
             }
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfb_ = clock64() + (long long)(m == 1.2345e-300);
 #endif
-            double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
+            double sigma = 1.0, my_sp = 0.0;
             // (unrolled: one problem per CTA is latency-bound, the compile-time shuffle lanes save the index arithmetic of the
             //  rolled loop that the throughput kernel prefers for its instruction-cache footprint)
 #ifdef B2_CTA_ROLL_CHOL
@@ -529,9 +535,7 @@ struct CtaSolver {
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (cc <= mi ? cc : mi));
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (cc <= mj ? cc : mj));
                 const bool ok = pv_ > 0.0;
-                const double sp = ok ? sigma * pv_ : 0.0;
-                if (cc == 0) sp0 = sp;
-                if (mj == cc) my_sp = sp;
+                if (mj == cc) my_sp = ok ? sigma * pv_ : 0.0;
                 if (ok) {
                     // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
                     // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
@@ -541,28 +545,50 @@ struct CtaSolver {
                     sigma *= pv_ * scale;
                 }
             }
-            // 1/sqrt(x) = sqrt(x) * (1/x): the square root and the reciprocal run side by side (both correctly rounded
-            // operations, like the mirror's), one multiplication after the slower of the two instead of a division after the root
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfc_ = clock64() + (long long)(m == 1.2345e-300);
 #endif
-            const double myrs = my_sp > 0.0 ? sqrt(my_sp) * (1.0 / my_sp) : 0.0;
-            m *= myrs;
-            const double rs0 = b2_bcast(myrs, 0);
-            const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double((1023 - (((__double2hiint(sp0) >> 20) & 0x7ff) - 1023)) << 20, 0) : 1.0;
-            const double rs1 = sig1 * b2_bcast(myrs, 2);
-            if (kk < N && lane == 0) { S(o.lamu + 0, kk) = rs0; S(o.lamu + 2, kk) = rs1; }
             if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;
             if (kk > 0) {
                 if (xx) S(xrow, kk) = m;
                 if (xu) S(lrow, kk) = m;
             }
+            if (dg) S(sprow, kk) = my_sp;
             __syncwarp();
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfe_ = clock64();
             clk_fa += tfa_ - tf0_; clk_fb += tfb_ - tfa_; clk_fc += tfc_ - tfb_; clk_fe += tfe_ - tfc_;
 #endif
         }
+    }
+
+    // end of the factorisation, all threads of the CTA, one (node, column) pair each: L_ic = S_ic / sqrt(sigma_c p_c), 1/L00, 1/L11
+    // (see mpc_wpp.cuh normalize_factor(); the thread of control column 0 handles both control columns, whose scales it overwrites)
+    __device__ void normalize_factor()
+    {
+        for (int e = tid; e < 7 * (N + 1); e += NTHR) {
+            const int kk = e / 7, cq = e - 7 * kk;
+            if (cq == 1) continue;
+            if (cq == 0) {
+                const double sp0 = S(o.lamu + 0, kk), sp1 = S(o.lamu + 2, kk);
+                const double rs0 = sp0 > 0.0 ? 1.0 / sqrt(sp0) : 0.0, rs1 = sp1 > 0.0 ? 1.0 / sqrt(sp1) : 0.0;
+                if (kk < N) {
+                    const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double(0x7fe00000 - (__double2hiint(sp0) & 0x7ff00000), 0) : 1.0;
+                    S(o.lamu + 0, kk) = rs0; S(o.lamu + 2, kk) = sig1 * rs1;
+                    S(o.lamu + 1, kk) *= rs0;
+                }
+                if (kk > 0) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) { S(o.lxu + 2 * i, kk) *= rs0; S(o.lxu + 2 * i + 1, kk) *= rs1; }
+                }
+            } else if (kk > 0) {
+                const int j = cq - 2;
+                const double spj = S(o.lrb + j, kk);
+                const double rsj = spj > 0.0 ? 1.0 / sqrt(spj) : 0.0;
+                for (int i = j; i < 5; i++) S(o.lxx + b2_sym(i, j), kk) *= rsj;
+            }
+        }
+        __syncthreads();
     }
 
     // q_lg, q_ug and rho_l, rho_u of obstacle j at node k (base kinds)
@@ -1172,7 +1198,10 @@ struct CtaSolver {
 #ifdef B2_DEBUG_CLOCK
             const long long c0_ = clock64();
 #endif
-            if (node_warp()) { riccati_factorize(); feedback_matrices(); }
+            if (node_warp()) riccati_factorize();
+            __syncthreads();
+            normalize_factor();
+            if (node_warp()) feedback_matrices();
             __syncthreads();
             scan_products();
 #ifdef B2_DEBUG_CLOCK

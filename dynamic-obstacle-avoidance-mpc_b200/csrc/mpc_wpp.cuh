@@ -145,7 +145,7 @@ struct WOff {
 
 __host__ __device__ inline int b2_wpp_stride(int N) { return (N + 1) | 1; }          // odd shared-memory row stride
 __host__ __device__ inline int b2_wpp_gstride(int N) { return N + 1; }               // global rows packed (footprint over sector alignment)
-#define B2_WPP_SCRATCH 40                                                             // flat doubles after the rows (AL, 7x5)
+#define B2_WPP_SCRATCH 80                                                             // flat doubles after the rows (U = [B A]^T S 7x5 at 0, U D at 40)
 __host__ __device__ inline size_t b2_wpp_smem_bytes(int N, int M, unsigned long long smask, bool sqp = false)
 {
     return sizeof(double) * ((size_t)WOff(M, smask, sqp).total * b2_wpp_stride(N) + B2_WPP_SCRATCH);
@@ -641,54 +641,63 @@ struct WppSolver {
         int mi = 0;
         while ((mi + 1) * (mi + 2) / 2 <= e) mi++;
         const int mj = e - mi * (mi + 1) / 2;
-        // phase A roles: lane owns AL entry (ai,aq) = lane, lanes 0..2 additionally entry 32+lane
-        const int ai0 = lane / 5, aq0 = lane % 5, ai1 = (32 + lane) / 5, aq1 = (32 + lane) % 5;
+        // phase A roles: lane < 30 owns entry (ai, aq) = (lane / 5, lane % 5) of U, lanes 0..4 additionally entry (6, lane)
+        const int ai0 = lane < 30 ? lane / 5 : 0, aq0 = lane % 5;
         int ba0[5], ba1[5];
 #pragma unroll
-        for (int r = 0; r < 5; r++) { ba0[r] = o.sv + B2_BATAB[r][ai0]; ba1[r] = o.sv + B2_BATAB[r][ai1 < 7 ? ai1 : 0]; }
+        for (int r = 0; r < 5; r++) { ba0[r] = o.sv + B2_BATAB[r][ai0]; ba1[r] = o.sv + B2_BATAB[r][6]; }
         const bool xx = lane < 28 && mi >= 2 && mj >= 2;
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
         const int xrow = xx ? o.lxx + b2_sym(mi - 2, mj - 2) : 0;
         const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
+        // the diagonal lane of column c keeps sigma_c p_c (the square of the column's normalisation) in a row of its own: the
+        // two control columns in the rows that will hold 1/L00 and 1/L11, the state columns in the rows of the refinement
+        // right-hand side (lrb), which are dead until lin_residuals() runs
+        const bool dg = lane < 28 && mi == mj;
+        const int sprow = mj == 0 ? o.lamu + 0 : mj == 1 ? o.lamu + 2 : o.lrb + (mj - 2);
         double* const scr = sm + o.total * NS;
         for (int kk = N; kk >= 0; kk--) {
             double m = 0.0;
             if (mi == mj) m = S(o.cv + mi, kk);                 // condensed node Hessian, left there by head()
             if (mi == 3 && mj == 2) m = S(o.hg + 7, kk);
             if (kk < N) {
-                // A: AL = [B A]^T Lxx(kk+1)
+                // A: U = [B A]^T Sxx(kk+1) with the UNNORMALISED factor Sxx = Lxx D^-1 of the next node, and U D^2 with
+                // D_q^2 = 1 / (sigma_q p_q): AL AL^T = U D^2 U^T needs one division per column and no square root, so the
+                // normalisation of the factor (square roots, 28 products, stores: normalize_factor()) leaves the sequential chain
                 {
+                    const double spq = S(o.lrb + aq0, kk + 1);
+                    const double dq = spq > 0.0 ? 1.0 / spq : 0.0;
                     double acc = 0.0;
 #pragma unroll
                     for (int r = 0; r < 5; r++) {
                         const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
                         acc = fma(S(ba0[r], kk), l, acc);
                     }
-                    scr[lane] = acc;
-                    if (lane < 3) {
+                    if (lane < 30) { scr[lane] = acc; scr[40 + lane] = acc * dq; }
+                    if (lane < 5) {
                         double acc1 = 0.0;
 #pragma unroll
                         for (int r = 0; r < 5; r++) {
-                            const double l = (r >= aq1) ? S(o.lxx + b2_sym(r, aq1 <= r ? aq1 : r), kk + 1) : 0.0;
+                            const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
                             acc1 = fma(S(ba1[r], kk), l, acc1);
                         }
-                        scr[32 + lane] = acc1;
+                        scr[30 + lane] = acc1; scr[70 + lane] = acc1 * dq;
                     }
                 }
                 __syncwarp();
-                // B: M = Htilde + AL AL^T
+                // B: M = Htilde + (U D^2) U^T
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 5; q++) acc = fma(scr[mi * 5 + q], scr[mj * 5 + q], acc);
+                for (int q = 0; q < 5; q++) acc = fma(scr[40 + mi * 5 + q], scr[mj * 5 + q], acc);
                 m += acc;
             }
             // C: right-looking Cholesky with DELAYED NORMALISATION.  The sequential chain per column is one
             // shuffle round + two FMAs: instead of T_ik -= T_ic T_kc / T_cc (rsqrt/division on the critical
             // path) the scaled Schur complement S = sigma * T is updated fraction-free,
             //     S_ik <- (S_ik p - S_ic S_kc) * 2^-e(p),   sigma <- sigma * p 2^-e(p),   p = S_cc,
-            // (the power of two keeps sigma in [1, 2^7)), and each lane normalises its own column once at
-            // the end: L_ic = S_ic / sqrt(sigma_c p_c).  Non-positive pivot -> zero column, as BLASFEO.
-            double sigma = 1.0, my_sp = 0.0, sp0 = 0.0;
+            // (the power of two keeps sigma in [1, 2^7)); column c of the factor is L_ic = S_ic / sqrt(sigma_c p_c), formed
+            // by normalize_factor() after the recursion.  Non-positive pivot -> zero column, as BLASFEO.
+            double sigma = 1.0, my_sp = 0.0;
             // rolled: the unrolled 7 columns made the loop body 5.9 KB, the size of an L0 instruction cache that three
             // warps share (measured +0.6 % at 4096 problems, +2.2 % at 32 768; same arithmetic)
 #pragma unroll 1
@@ -697,9 +706,7 @@ struct WppSolver {
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (c <= mj ? c : mj));
                 const bool ok = pv_ > 0.0;
-                const double sp = ok ? sigma * pv_ : 0.0;
-                if (c == 0) sp0 = sp;
-                if (mj == c) my_sp = sp;
+                if (mj == c) my_sp = ok ? sigma * pv_ : 0.0;
                 if (ok) {
                     // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
                     // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
@@ -709,22 +716,48 @@ struct WppSolver {
                     sigma *= pv_ * scale;
                 }
             }
-            // one rsqrt per lane (its own column); 1/L00 and 1/L11 come from the diagonal lanes 0 and 2:
-            //   1/L00 = rsqrt(p_0),  1/L11 = sqrt(sigma_1/p_1) = sigma_1 rsqrt(sigma_1 p_1),  sigma_1 = p_0 2^-e(p_0)
-            // 1/sqrt through the two correctly rounded operations (rsqrt() is not: the CPU mirror could not reproduce it)
-            const double myrs = my_sp > 0.0 ? 1.0 / sqrt(my_sp) : 0.0;
-            m *= myrs;
-            const double rs0 = b2_bcast(myrs, 0);
-            const double sig1 = sp0 > 0.0 ? sp0 * __hiloint2double((1023 - (((__double2hiint(sp0) >> 20) & 0x7ff) - 1023)) << 20, 0) : 1.0;
-            const double rs1 = sig1 * b2_bcast(myrs, 2);
-            if (kk < N && lane == 0) { S(o.lamu + 0, kk) = rs0; S(o.lamu + 2, kk) = rs1; }
-            if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;                 // l10
+            // unnormalised column entries and the column scales; normalize_factor() turns them into L, 1/L00, 1/L11
+            if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;                 // S10
             if (kk > 0) {
                 if (xx) S(xrow, kk) = m;
                 if (xu) S(lrow, kk) = m;
             }
+            if (dg) S(sprow, kk) = my_sp;
             __syncwarp();
         }
+        normalize_factor();
+    }
+
+    // node-parallel end of the factorisation: L_ic = S_ic / sqrt(sigma_c p_c) for the stored columns (Lxu, Lxx; l10),
+    //   1/L00 = 1 / sqrt(p_0),  1/L11 = sqrt(sigma_1 / p_1) = sigma_1 / sqrt(sigma_1 p_1),  sigma_1 = p_0 2^-e(p_0).
+    // 1/sqrt through the two correctly rounded operations (rsqrt() is not: the CPU mirror could not reproduce it).
+    __device__ void normalize_factor()
+    {
+        for (k = lane; k <= N; k += 32) {
+            double sig1 = 1.0;
+            // (rolled: one copy of the square root / division sequences in the instruction stream)
+#pragma unroll 1
+            for (int c = 0; c < 7; c++) {
+                const int row = c == 0 ? o.lamu : c == 1 ? o.lamu + 2 : o.lrb + c - 2;
+                const double sp = S(row, k);
+                const double rs = sp > 0.0 ? 1.0 / sqrt(sp) : 0.0;
+                if (c == 0) {
+                    sig1 = sp > 0.0 ? sp * __hiloint2double(0x7fe00000 - (__double2hiint(sp) & 0x7ff00000), 0) : 1.0;
+                    if (k < N) { S(o.lamu + 0, k) = rs; S(o.lamu + 1, k) *= rs; }
+                }
+                if (c == 1 && k < N) S(o.lamu + 2, k) = sig1 * rs;
+                if (k > 0) {
+                    if (c < 2) {
+#pragma unroll
+                        for (int i = 0; i < 5; i++) S(o.lxu + 2 * i + c, k) *= rs;
+                    } else {
+#pragma unroll 1
+                        for (int i = c - 2; i < 5; i++) S(o.lxx + i * (i + 1) / 2 + (c - 2), k) *= rs;
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
 
     // complementarity right-hand side of a base solve: kind 0 (affine) lam t; 1 (corrector) lam t + dt_aff dlam_aff - sigma mu;
