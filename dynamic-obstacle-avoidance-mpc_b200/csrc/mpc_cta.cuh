@@ -499,16 +499,15 @@ struct CtaSolver {
                         const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
                         acc = fma(S(ba0[r], kk), l, acc);
                     }
-                    if (lane < 30) { scr[lane] = acc; scr[40 + lane] = acc * dq; }
-                    if (lane < 5) {
-                        double acc1 = 0.0;
+                    // (row 6 of U: computed by every lane, stored by lanes 0..4 -- no divergent branch inside the recursion)
+                    double acc1 = 0.0;
 #pragma unroll
-                        for (int r = 0; r < 5; r++) {
-                            const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
-                            acc1 = fma(S(ba1[r], kk), l, acc1);
-                        }
-                        scr[30 + lane] = acc1; scr[70 + lane] = acc1 * dq;
+                    for (int r = 0; r < 5; r++) {
+                        const double l = (r >= aq0) ? S(o.lxx + b2_sym(r, aq0 <= r ? aq0 : r), kk + 1) : 0.0;
+                        acc1 = fma(S(ba1[r], kk), l, acc1);
                     }
+                    if (lane < 30) { scr[lane] = acc; scr[40 + lane] = acc * dq; }
+                    if (lane < 5) { scr[30 + lane] = acc1; scr[70 + lane] = acc1 * dq; }
                 }
                 __syncwarp();
 #ifdef B2_DEBUG_CLOCK_FACT
@@ -536,14 +535,24 @@ struct CtaSolver {
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (cc <= mj ? cc : mj));
                 const bool ok = pv_ > 0.0;
                 if (mj == cc) my_sp = ok ? sigma * pv_ : 0.0;
+#ifdef B2_CHOL_BRANCH
                 if (ok) {
-                    // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
-                    // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
-                    // of two commutes with the rounding), one multiplication shorter on the dependent chain
                     const double scale = __hiloint2double(0x7fe00000 - (__double2hiint(pv_) & 0x7ff00000), 0);
                     if (mj > cc) m = fma(m, pv_, -(la * lb)) * scale;
                     sigma *= pv_ * scale;
                 }
+#else
+                {
+                    // scale = 2^-e(p): exponent field 2046 - e, i.e. 0x7fe00000 - (high word & 0x7ff00000) (p > 0, finite).  The
+                    // update is written as fma(m, p, -(la lb)) * scale: bit-identical to fma(m, p scale, -(la lb) scale) (a power
+                    // of two commutes with the rounding), one multiplication shorter on the dependent chain.  Branch-free: a
+                    // non-positive (or NaN) pivot leaves m and sigma as they are by selects, not by a divergent branch
+                    const double scale = __hiloint2double(0x7fe00000 - (__double2hiint(pv_) & 0x7ff00000), 0);
+                    const double mn = fma(m, pv_, -(la * lb)) * scale, sn = sigma * (pv_ * scale);
+                    m = (ok && mj > cc) ? mn : m;
+                    sigma = ok ? sn : sigma;
+                }
+#endif
             }
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfc_ = clock64() + (long long)(m == 1.2345e-300);
