@@ -339,7 +339,7 @@ def main():
         lat_detail = {"p50_ms": lat1, "p90_ms": float(np.quantile(lat_all, 0.9)), "min_ms": float(lat_all.min()), "max_ms": float(lat_all.max()),
                       "problems": n_lat, "median_qp_iter": float(np.median([int(t.item()) for t in its1])),
                       "scenario_0_ms": float(np.median(lat_all[0::n_lat])),
-                      "what": "device time of b2mpc_solve(batch = 1) incl. its two queue kernels, median over the first "
+                      "what": "device time of b2mpc_solve(batch = 1) (one launch: a single problem skips the queue kernels), median over the first "
                               f"{n_lat} scenarios of the workload x 2 timed rounds"}
         # BASELINE config 1: one closed-loop episode (B = 1), ms per control step through the fused entry
         sc1 = {k: np.ascontiguousarray(v[:1]) for k, v in sc.items()}
