@@ -531,6 +531,28 @@ struct WppSolver {
             const double Zuq = sc * p.Zu;
             double vo2 = 0.0, vo3 = 0.0, dv2 = 0.0, dv3 = 0.0;
             if (B2_WPP_NO_DT) { vo2 = S(o.cv + 2, k); vo3 = S(o.cv + 3, k); dv2 = R<PF_DV>(2, k); dv3 = R<PF_DV>(3, k); }
+            // everything that the obstacles do not touch is finished here and leaves the registers before their loop: the
+            // dynamics residual, and every component of the stationarity residual / condensed Hessian / affine right-hand side
+            // but the two position components
+            if (k < N) {
+                double rb[5];
+                b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    rb[i] += Q<PF_B>(i) - VV(2 + i, k + 1);
+                    S(o.rb + i, k) = rb[i];
+                    n1 = fmax(n1, fabs(rb[i]));
+                }
+            }
+            if (k == 0) { rg[4] = rg[5] = rg[6] = 0.0; }
+            if (k == N) { rg[0] = rg[1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                if (i == 2 || i == 3) continue;
+                Q<PF_RG>(i) = rg[i]; n0 = fmax(n0, fabs(rg[i]));
+                S(o.hg + i, k) = rg[i] + gt[i];
+                S(o.cv + i, k) = Hx[i];
+            }
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
                 prefetch_ahead<FM_HEAD>(j);
@@ -606,20 +628,9 @@ struct WppSolver {
                 const double coef = fma(-(Gl * rhol), Dli, q0) - fma(-(Gu * rhou), Dui, q1);
                 gt[2] = fma(cx, coef, gt[2]); gt[3] = fma(cy, coef, gt[3]);
             }
-            if (k < N) {
-                double rb[5];
-                b2_ba_mul(sv, p.dt, p.dt2h, v, rb);
+            if (k == 0) { rg[2] = rg[3] = 0.0; }
 #pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    rb[i] += Q<PF_B>(i) - VV(2 + i, k + 1);
-                    S(o.rb + i, k) = rb[i];
-                    n1 = fmax(n1, fabs(rb[i]));
-                }
-            }
-            if (k == 0) { rg[2] = rg[3] = rg[4] = rg[5] = rg[6] = 0.0; }
-            if (k == N) { rg[0] = rg[1] = 0.0; }
-#pragma unroll
-            for (int i = 0; i < 7; i++) {
+            for (int i = 2; i < 4; i++) {
                 Q<PF_RG>(i) = rg[i]; n0 = fmax(n0, fabs(rg[i]));
                 S(o.hg + i, k) = rg[i] + gt[i];
                 S(o.cv + i, k) = Hx[i];
@@ -813,8 +824,7 @@ struct WppSolver {
             const double sc = scal(k);
             double gt[7];
             if (kind == 3) {
-#pragma unroll
-                for (int i = 0; i < 7; i++) gt[i] = S(o.hg + i, k);          // lin_residuals left lrg here
+                gt[2] = S(o.hg + 2, k); gt[3] = S(o.hg + 3, k);                // the linear residual lrg is in hg: the obstacles add to two rows
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
                     prefetch_ahead<FM_PREP3>(j);
@@ -840,6 +850,11 @@ struct WppSolver {
                     const double qu = fma(lu_, rdu, rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu)) * Q<PF_TINV>(iu);
                     slot_add(gt, s, ql - qu);
                 }
+                // (the components that the obstacles do not touch leave the registers before their loop)
+#pragma unroll
+                for (int i = 0; i < 7; i++) {
+                    if (i != 2 && i != 3) S(o.hg + i, k) = gt[i];
+                }
                 const double Zuq = sc * p.Zu;
 #pragma unroll JU
             for (int j = 0; j < M; j++) {
@@ -852,8 +867,7 @@ struct WppSolver {
                     gt[3] = fma(Q<PF_CY>(j), coef, gt[3]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 7; i++) S(o.hg + i, k) = gt[i];
+            S(o.hg + 2, k) = gt[2]; S(o.hg + 3, k) = gt[3];
         }
         __syncwarp();
     }
