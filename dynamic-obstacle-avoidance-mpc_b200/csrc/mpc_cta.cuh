@@ -478,6 +478,8 @@ struct CtaSolver {
         const bool xu = lane < 28 && mi >= 2 && mj < 2;
         const int xrow = xx ? o.lxx + b2_sym(mi - 2, mj - 2) : 0;
         const int lrow = xu ? o.lxu + 2 * (mi - 2) + mj : 0;
+        const bool mine = xx || xu || lane == 1;
+        const int myrow = xx ? xrow : xu ? lrow : o.lamu + 1;
         const bool dg = lane < 28 && mi == mj;
         const int sprow = mj == 0 ? o.lamu + 0 : mj == 1 ? o.lamu + 2 : o.lrb + (mj - 2);
         double* const scr = sm + (o.total + PHI_ROWS) * NS;
@@ -557,11 +559,7 @@ struct CtaSolver {
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfc_ = clock64() + (long long)(m == 1.2345e-300);
 #endif
-            if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;
-            if (kk > 0) {
-                if (xx) S(xrow, kk) = m;
-                if (xu) S(lrow, kk) = m;
-            }
+            if (mine) S(myrow, kk) = m;                                  // (see mpc_wpp.cuh: loop-invariant predicate)
             if (dg) S(sprow, kk) = my_sp;
             __syncwarp();
 #ifdef B2_DEBUG_CLOCK_FACT

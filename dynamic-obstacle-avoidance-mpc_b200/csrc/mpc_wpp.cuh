@@ -668,6 +668,8 @@ struct WppSolver {
         // the diagonal lane of column c keeps sigma_c p_c (the square of the column's normalisation) in a row of its own: the
         // two control columns in the rows that will hold 1/L00 and 1/L11, the state columns in the rows of the refinement
         // right-hand side (lrb), which are dead until the linear residual is assembled
+        const bool mine = xx || xu || lane == 1;                        // S10 (lane 1), Sxu, Sxx
+        const int myrow = xx ? xrow : xu ? lrow : o.lamu + 1;
         const bool dg = lane < 28 && mi == mj;
         const int sprow = mj == 0 ? o.lamu + 0 : mj == 1 ? o.lamu + 2 : o.lrb + (mj - 2);
         double* const scr = sm + o.total * NS;
@@ -741,11 +743,9 @@ struct WppSolver {
 #endif
             }
             // unnormalised column entries and the column scales; normalize_factor() turns them into L, 1/L00, 1/L11
-            if (kk < N && lane == 1) S(o.lamu + 1, kk) = m;                 // S10
-            if (kk > 0) {
-                if (xx) S(xrow, kk) = m;
-                if (xu) S(lrow, kk) = m;
-            }
+            // (one store per lane under a loop-invariant predicate; the rows of node 0 / the terminal node that nobody reads are
+            //  written too, which keeps lane- and node-dependent branches out of the recursion)
+            if (mine) S(myrow, kk) = m;
             if (dg) S(sprow, kk) = my_sp;
             __syncwarp();
         }
@@ -964,12 +964,12 @@ struct WppSolver {
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double lu0 = w0 * l00i;
             const double lu1 = fma(-l10, lu0, w1) * l11i;
-            if (lane == 0) { S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1; }
+            S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1;           // (every lane holds the 2-vector: same value, same address)
             if (kk > 0) {
                 const double pa = fma(S(acol[0], kk), s[0], S(o.hg + 2 + c5, kk)) + fma(S(acol[1], kk), s[1], S(acol[2], kk) * s[2]);
                 const double pb = fma(S(acol[3], kk), s[3], S(acol[4], kk) * s[4]);
                 const double pc = (pa + pb) - fma(S(o.lxu + 2 * c5, kk), lu0, S(o.lxu + 2 * c5 + 1, kk) * lu1);
-                if (lane < 5) R<PF_PV>(lane, kk) = pc;
+                R<PF_PV>(c5, kk) = pc;                              // (lanes >= 5 recompute component 4: no divergent store)
 #pragma unroll
                 for (int r = 0; r < 5; r++) pf[r] = b2_bcast(pc, r);
             }
@@ -993,8 +993,8 @@ struct WppSolver {
             const double du0 = fma(-l10, du1, -r0) * l00i;
             const double xa = fma(S(arow[3], kk), dx[1], fma(S(arow[2], kk), dx[0], S(oRB + c5, kk))) + fma(S(arow[6], kk), dx[4], fma(S(arow[5], kk), dx[3], S(arow[4], kk) * dx[2]));
             const double xn = xa + fma(S(arow[0], kk), du0, S(arow[1], kk) * du1);
-            if (lane == 0) { rDV(0, kk) = du0; rDV(1, kk) = du1; }
-            if (lane < 5) rDV(2 + lane, kk + 1) = xn;
+            rDV(0, kk) = du0; rDV(1, kk) = du1;
+            rDV(2 + c5, kk + 1) = xn;
 #pragma unroll
             for (int r = 0; r < 5; r++) dx[r] = b2_bcast(xn, r);
         }
