@@ -526,12 +526,15 @@ struct CtaSolver {
             double sigma = 1.0, my_sp = 0.0;
             // (unrolled: one problem per CTA is latency-bound, the compile-time shuffle lanes save the index arithmetic of the
             //  rolled loop that the throughput kernel prefers for its instruction-cache footprint)
+            // (Experiment, negative: TWO columns per exchange round -- 7 broadcasts, the second step's pivot and column entries
+            //  recomputed by every lane that needs them, bit-identical -- halves the dependent exchange rounds but adds 9 FP64
+            //  operations per lane and pair: 0.818 against 0.811 ms.  The rounds are issue-bound, not latency-bound.)
 #ifdef B2_CTA_ROLL_CHOL
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-            for (int cc = 0; cc < 7; cc++) {
+            for (int cc = 0; cc < 6; cc++) {
                 const double pv_ = b2_bcast(m, cc * (cc + 1) / 2 + cc);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (cc <= mi ? cc : mi));
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (cc <= mj ? cc : mj));
@@ -556,6 +559,8 @@ struct CtaSolver {
                 }
 #endif
             }
+            // (the last column has nothing below or to the right of its pivot: its lane needs sigma and its own entry, no exchange)
+            if (mj == 6) my_sp = m > 0.0 ? sigma * m : 0.0;
 #ifdef B2_DEBUG_CLOCK_FACT
             const long long tfc_ = clock64() + (long long)(m == 1.2345e-300);
 #endif

@@ -717,7 +717,7 @@ struct WppSolver {
             // rolled: the unrolled 7 columns made the loop body 5.9 KB, the size of an L0 instruction cache that three
             // warps share (measured +0.6 % at 4096 problems, +2.2 % at 32 768; same arithmetic)
 #pragma unroll 1
-            for (int c = 0; c < 7; c++) {
+            for (int c = 0; c < 6; c++) {
                 const double pv_ = b2_bcast(m, c * (c + 1) / 2 + c);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (c <= mj ? c : mj));
@@ -742,6 +742,8 @@ struct WppSolver {
                 }
 #endif
             }
+            // (the last column has nothing below or to the right of its pivot: its lane needs sigma and its own entry, no exchange)
+            if (mj == 6) my_sp = m > 0.0 ? sigma * m : 0.0;
             // unnormalised column entries and the column scales; normalize_factor() turns them into L, 1/L00, 1/L11
             // (one store per lane under a loop-invariant predicate; the rows of node 0 / the terminal node that nobody reads are
             //  written too, which keeps lane- and node-dependent branches out of the recursion)

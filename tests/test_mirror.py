@@ -108,3 +108,23 @@ def test_cta_kernel_mirror_matches_oracle_and_warp_kernel(mirror, oracle, N, tf,
     for k in ("lam", "pi"):
         assert _rel_rows(o4[k], d[k])[sel].max() < 1e-5, k
     assert np.mean(o4["qp_iter"] == res[2][1]["qp_iter"]) >= 0.95
+
+
+def test_long_horizon_mirror_matches_oracle(mirror, oracle):
+    """BASELINE config 4 (N = 100, 20 obstacles) on the CPU: the `<20,100,LONG>` instantiation -- node-private rows AND v, pi, dv,
+    dpi in "global" memory, four node rounds per pass, the linear-residual pass fused into the expansion pass (FUSE_LIN), the
+    software prefetch (a no-op in the emulator) -- against the independent oracle on a handful of problems."""
+    N, M, tf, B = 100, 20, 5.0, 12
+    dims = world.MpcDims(N, M, tf)
+    sc = world.random_scenarios(B, dims, seed=8)
+    m = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    out = mirror.solve_batch(mirror.default_config(N, M, tf), sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], m["x"], m["u"], m["sl"], m["su"])
+    r = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    st, it, _ = oracle.rti_solve_batch(oracle.default_config(N, M, tf), sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"],
+                                       r["x"], r["u"], r["sl"], r["su"], nthreads=4)
+    assert (out["status"] == st).all()
+    assert (out["qp_iter"] != it).sum() <= 1 and np.abs(out["qp_iter"] - it).max() <= 1
+    sel = (st == 0) & (it < 50) & (out["qp_iter"] < 50)
+    assert sel.sum() >= 2
+    for k in ("u", "x"):
+        assert _rel_rows(m[k], r[k])[sel].max() < 1e-6, k
