@@ -529,12 +529,7 @@ struct CtaSolver {
             // (Experiment, negative: TWO columns per exchange round -- 7 broadcasts, the second step's pivot and column entries
             //  recomputed by every lane that needs them, bit-identical -- halves the dependent exchange rounds but adds 9 FP64
             //  operations per lane and pair: 0.818 against 0.811 ms.  The rounds are issue-bound, not latency-bound.)
-#ifdef B2_CTA_ROLL_CHOL
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-            for (int cc = 0; cc < 6; cc++) {
+            auto column = [&](const int cc) {
                 const double pv_ = b2_bcast(m, cc * (cc + 1) / 2 + cc);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (cc <= mi ? cc : mi));
                 const double lb = b2_bcast(m, mj * (mj + 1) / 2 + (cc <= mj ? cc : mj));
@@ -558,6 +553,11 @@ struct CtaSolver {
                     sigma = ok ? sn : sigma;
                 }
 #endif
+            };
+            column(0); column(1);
+            if (kk > 0) {                                                // (node 0: the state is eliminated, only the control block is used)
+#pragma unroll
+                for (int cc = 2; cc < 6; cc++) column(cc);
             }
             // (the last column has nothing below or to the right of its pivot: its lane needs sigma and its own entry, no exchange)
             if (mj == 6) my_sp = m > 0.0 ? sigma * m : 0.0;
