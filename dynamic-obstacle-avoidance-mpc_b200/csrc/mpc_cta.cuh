@@ -3,13 +3,14 @@
 //
 // mpc_wpp.cuh gives a problem ONE warp: the node-parallel passes of an interior-point iteration (KKT residuals, barrier /
 // slack elimination, expansion of the steps, step length) then walk the 6 box slots and M obstacles of a node sequentially,
-// and the lanes beyond N+1 idle.  Here a problem owns a CTA and EVERYTHING of the problem lives in shared memory (57 KB: four
-// problems per SM, no scratch in global memory at all):
+// and the lanes beyond N+1 idle.  Here a problem owns a CTA and EVERYTHING of the problem lives in shared memory (78 KB at N = 20:
+// two problems per SM, no scratch in global memory at all):
 //   * obstacle warps (4 at N = 20, M = 5): one thread per (node, obstacle) -- its two general constraints and two slack
 //     bounds; the M obstacles of a node sit in adjacent lanes and their contributions to the node's condensed Hessian /
 //     gradient / residual are summed by a fixed shuffle tree, then handed to the node warp through shared memory;
-//   * node warp (the last one): one thread per node -- the node-level algebra and the six box slots -- and the sequential
-//     Riccati sweeps of mpc_wpp.cuh (lane = matrix entry / vector component) while the obstacle warps wait at the barrier;
+//   * node warp (the last one): one thread per node -- the node-level algebra and the six box slots -- and the Riccati
+//     recursion of mpc_wpp.cuh (lane = matrix entry) while the obstacle warps wait at the barrier; the two vector recursions of
+//     a solve are parallel scans over the nodes (B2_CTA_SCAN below);
 //   * problem-wide reductions (mu, step length, norms): warp butterfly -> shared memory -> every thread, in a fixed order.
 // Every warp has ONE role: a first version that mixed node-level and obstacle lanes in the same warp left the warps
 // permanently split into two convergence groups (measured: 5 active lanes inside the sweeps, every shuffle through the
@@ -1315,7 +1316,7 @@ struct CtaSolver {
 };
 
 #ifndef B2_CTA_MINB
-#define B2_CTA_MINB 2           // resident CTAs per SM the kernel is compiled for: 168 registers.  (61 KB of shared memory per problem
+#define B2_CTA_MINB 2           // resident CTAs per SM the kernel is compiled for: 168 registers.  (78 KB of shared memory per problem
                                 // would allow 3 at 128 registers: measured 6.5 % slower per problem, 1.426 vs 1.333 ms)
 #endif
 // dynamic shared memory of the CTA kernel: the shared rows of the chosen placement (mpc_wpp.cuh WOff) + the Phi rows + scratch
@@ -1325,7 +1326,7 @@ __host__ __device__ inline size_t b2_cta_smem_bytes(int N, int M, unsigned long 
 }
 
 // MINB: resident CTAs per SM the instantiation is compiled for (register budget 65536 / (MINB * threads)).
-//   latency kernel  <5, N, 0, ALL_SHARED, 2>: 168 registers (61 KB of shared memory per problem would allow 3 CTAs at 128
+//   latency kernel  <5, N, 0, ALL_SHARED, 2>: 168 registers (78 KB of shared memory per problem; at 61 KB, before the scan products, 3 CTAs at 128
 //                                             registers: measured 6.5 % slower per problem, 1.426 vs 1.333 ms)
 //   throughput candidates <5, 20, 1 or 2, ALL_GLOBAL, 8 or 6>: node-private rows in L2 like the warp kernel, 22 KB of shared memory
 template <int MT, int NT, int NOW_ = 0, unsigned long long SMASK_ = B2_WPP_ALL_SHARED, int MINB = 2>
