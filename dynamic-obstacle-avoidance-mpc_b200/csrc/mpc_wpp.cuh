@@ -93,6 +93,9 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 #ifndef B2_WPP_PFD
 #define B2_WPP_PFD 1
 #endif
+#ifndef B2_WPP_FEEDBACK_GAIN
+#define B2_WPP_FEEDBACK_GAIN 0   // experiment: G = Lxu Luu^-1 formed once per factorisation, no triangular solve inside the sweeps
+#endif
 #ifndef B2_WPP_FUSE_LIN
 #define B2_WPP_FUSE_LIN 1        // 0 never, 1 horizons > 32 nodes, 2 always: the linear-residual pass fused into the expansion pass
 #endif
@@ -782,6 +785,20 @@ struct WppSolver {
                     }
                 }
             }
+#if B2_WPP_FEEDBACK_GAIN
+            // feedback gain G_k = Lxu Luu^-1 (5 x 2), stored over Lxu (nothing else reads it): the KKT solves then need no
+            // triangular solve with Luu inside their sequential sweeps -- p_k = gx + A^T s - G (gu + B^T s) going backward,
+            // du_k = du0_k - G^T dx_k going forward, du0_k = -(Luu Luu^T)^-1 w_k formed node-parallel in between
+            if (k > 0 && k < N) {
+                const double l00i = S(o.lamu + 0, k), l10 = S(o.lamu + 1, k), l11i = S(o.lamu + 2, k);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const double g1 = S(o.lxu + 2 * i + 1, k) * l11i;
+                    const double g0 = fma(-g1, l10, S(o.lxu + 2 * i, k)) * l00i;
+                    S(o.lxu + 2 * i, k) = g0; S(o.lxu + 2 * i + 1, k) = g1;
+                }
+            }
+#endif
         }
         __syncwarp();
     }
@@ -963,9 +980,13 @@ struct WppSolver {
             // short dependency trees: the chain through this loop is the critical path of a solve
             const double w0 = fma(S(o.sv + SV_B00, kk), s[0], S(o.hg + 0, kk)) + fma(S(o.sv + SV_B10, kk), s[1], h * s[3]);
             const double w1 = fma(h, s[4], fma(S(o.sv + SV_B01, kk), s[0], S(o.hg + 1, kk)) + fma(S(o.sv + SV_B11, kk), s[1], h2 * s[2]));
+#if B2_WPP_FEEDBACK_GAIN
+            const double lu0 = w0, lu1 = w1;                        // (G w instead of Lxu (Luu^-1 w))
+#else
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double lu0 = w0 * l00i;
             const double lu1 = fma(-l10, lu0, w1) * l11i;
+#endif
             S(o.lu + 0, kk) = lu0; S(o.lu + 1, kk) = lu1;           // (every lane holds the 2-vector: same value, same address)
             if (kk > 0) {
                 const double pa = fma(S(acol[0], kk), s[0], S(o.hg + 2 + c5, kk)) + fma(S(acol[1], kk), s[1], S(acol[2], kk) * s[2]);
@@ -981,10 +1002,29 @@ struct WppSolver {
             }
         }
         __syncwarp();
+#if B2_WPP_FEEDBACK_GAIN
+        // ---- between the sweeps, node-parallel: du0_k = -Luu^-T Luu^-1 w_k (over w_k)
+        for (k = lane; k < N; k += 32) {
+            const double l00i = S(o.lamu + 0, k), l10 = S(o.lamu + 1, k), l11i = S(o.lamu + 2, k);
+            const double lu0 = S(o.lu + 0, k) * l00i;
+            const double lu1 = fma(-l10, lu0, S(o.lu + 1, k)) * l11i;
+            const double d1 = -lu1 * l11i;
+            S(o.lu + 1, k) = d1;
+            S(o.lu + 0, k) = fma(-l10, d1, -lu0) * l00i;
+        }
+        __syncwarp();
+#endif
         // ---- forward
         double dx[5] = {0, 0, 0, 0, 0};
         if (lane < 5) rDV(2 + lane, 0) = 0.0;
         for (int kk = 0; kk < N; kk++) {
+#if B2_WPP_FEEDBACK_GAIN
+            double du0 = S(o.lu + 0, kk), du1 = S(o.lu + 1, kk);
+            if (kk > 0) {                                           // du = du0 - G^T dx
+                du0 -= fma(S(o.lxu + 2, kk), dx[1], S(o.lxu + 0, kk) * dx[0]) + fma(S(o.lxu + 8, kk), dx[4], fma(S(o.lxu + 6, kk), dx[3], S(o.lxu + 4, kk) * dx[2]));
+                du1 -= fma(S(o.lxu + 3, kk), dx[1], S(o.lxu + 1, kk) * dx[0]) + fma(S(o.lxu + 9, kk), dx[4], fma(S(o.lxu + 7, kk), dx[3], S(o.lxu + 5, kk) * dx[2]));
+            }
+#else
             double r0 = S(o.lu + 0, kk), r1 = S(o.lu + 1, kk);
             if (kk > 0) {
                 r0 = fma(S(o.lxu + 2, kk), dx[1], fma(S(o.lxu + 0, kk), dx[0], r0)) + fma(S(o.lxu + 8, kk), dx[4], fma(S(o.lxu + 6, kk), dx[3], S(o.lxu + 4, kk) * dx[2]));
@@ -993,6 +1033,7 @@ struct WppSolver {
             const double l00i = S(o.lamu + 0, kk), l10 = S(o.lamu + 1, kk), l11i = S(o.lamu + 2, kk);
             const double du1 = -r1 * l11i;
             const double du0 = fma(-l10, du1, -r0) * l00i;
+#endif
             const double xa = fma(S(arow[3], kk), dx[1], fma(S(arow[2], kk), dx[0], S(oRB + c5, kk))) + fma(S(arow[6], kk), dx[4], fma(S(arow[5], kk), dx[3], S(arow[4], kk) * dx[2]));
             const double xn = xa + fma(S(arow[0], kk), du0, S(arow[1], kk) * du1);
             rDV(0, kk) = du0; rDV(1, kk) = du1;
