@@ -801,6 +801,15 @@ __global__ void b2_order_keys(const double* __restrict__ X, const double* __rest
     key[b] = kk;
     atomicAdd(&hist[kk], 1);
 }
+__global__ void b2_order_keys_prev(const int32_t* __restrict__ it, int32_t* __restrict__ key, int32_t* __restrict__ hist, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int i = it[b];
+    const int kk = B2_ORDER_NODEKEYS - 1 - (i < B2_ORDER_NODEKEYS ? (i > 0 ? i : 0) : B2_ORDER_NODEKEYS - 1);
+    key[b] = kk;
+    atomicAdd(&hist[kk], 1);
+}
 // key < 0: the problem is not queued (closed loop: an environment that has reached its goal).  The first thread also
 // prepares what the persistent solve kernel and the NEXT scatter need: work counter, queue length, and -- the key
 // histogram being double-buffered between control steps -- zeroes of the other buffer.
@@ -928,6 +937,12 @@ static int solve_impl(b2mpc* h, int64_t batch, bool sqp, int32_t max_iter, const
     }
     CUDA_TRY(cudaMemsetAsync(o.hist[0], 0, (4 * B2_ORDER_MAXKEYS + 8) * sizeof(int32_t), st));
     const unsigned ob = (unsigned)((batch + 127) / 128);
+    static const int key_prev = []() { const char* e = getenv("B2MPC_SOLVE_KEY"); return (e && e[0] == 'p') ? 1 : 0; }();
+    if (key_prev)      // experiment (B2MPC_SOLVE_KEY=prev): the iteration counts of the PREVIOUS solve as queue keys -- with the same
+                       // problems solved twice from the same iterate this is the perfect cost predictor (upper bound of what a
+                       // better launch order can recover of the drain tail)
+        b2_order_keys_prev<<<ob, 128, 0, st>>>(h->fi[B2MPC_QP_ITER], o.key, o.hist[0], (int)batch);
+    else
     b2_order_keys<<<ob, 128, 0, st>>>(h->f[B2MPC_X], h->f[B2MPC_P], o.key, o.hist[0], h->N, h->M, h->cfg.r2, (int)batch, h->Bm);
     b2_order_scatter<<<ob, 128, 0, st>>>(o.key, o.hist[0], o.fill[0], o.order, B2_ORDER_NKEYS, (int)batch, nullptr, nullptr, nullptr, nullptr);
     h->launches += 2;
