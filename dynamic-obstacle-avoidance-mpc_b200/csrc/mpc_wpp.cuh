@@ -718,8 +718,13 @@ struct WppSolver {
             // by normalize_factor() after the recursion.  Non-positive pivot -> zero column, as BLASFEO.
             double sigma = 1.0, my_sp = 0.0;
             // rolled: the unrolled 7 columns made the loop body 5.9 KB, the size of an L0 instruction cache that three
-            // warps share (measured +0.6 % at 4096 problems, +2.2 % at 32 768; same arithmetic)
+            // warps share (measured +0.6 % at 4096 problems, +2.2 % at 32 768; same arithmetic).  End of round 2, six columns,
+            // -DB2_WPP_UNROLL_CHOL: 8150 -> 8520 instructions, 9.10 -> 9.29 ms per 4096 problems, 61.3 -> 63.3 ms per 32 768)
+#ifdef B2_WPP_UNROLL_CHOL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int c = 0; c < 6; c++) {
                 const double pv_ = b2_bcast(m, c * (c + 1) / 2 + c);
                 const double la = b2_bcast(m, mi * (mi + 1) / 2 + (c <= mi ? c : mi));
