@@ -157,6 +157,31 @@ def test_merit_backtracking_matches_oracle(torch_cuda, oracle):
     assert (out["nlp_res"][out["status"] == 0] < 1e-6).all()
 
 
+@pytest.mark.parametrize("glob", [0, 1])
+def test_sqp_is_bit_identical_to_the_mirror(torch_cuda, glob):
+    """against the independent oracle the line-search mode agrees on 80 % of the SQP iteration
+    counts -- the accept / reject decisions compare merit sums whose order differs.  Against the CPU mirror of the kernel SOURCE
+    (oracle/simt: same operations, same order) there is nothing left: iterates, multipliers, NLP residuals, statuses, SQP and
+    interior-point iteration counts of every problem are bit-identical, with and without the line search."""
+    from b200mpc import BatchedMpcSolver
+    from oracle import pymirror as pm
+    B, lm, max_iter = 48, 0.05, 15
+    sc = world.random_scenarios(B, DIMS, seed=14, moving_start=True)
+    s = BatchedMpcSolver(20, 5, 2.0, max_batch=B, lm=lm, nlp_solver=1, nlp_iter_max=max_iter, nlp_globalization=glob, kernel=2)
+    _load(torch_cuda, s, sc, B)
+    s.solve(B)
+    out = _read(s, B)
+    s.close()
+    cfg = pm.default_config(20, 5, 2.0, lm=lm, nlp_solver=1, nlp_iter_max=max_iter, nlp_globalization=glob)
+    m = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    mo = pm.solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], m["x"], m["u"], m["sl"], m["su"], layout=2, sqp=True)
+    for k in ("x", "u", "sl", "su"):
+        assert np.array_equal(out[k], m[k]), k
+    for k in ("pi", "lam", "t", "nlp_res", "status", "qp_iter", "sqp_iter"):
+        assert np.array_equal(out[k], mo[k]), k
+    assert (out["sqp_iter"] > 1).mean() > 0.9            # the outer loop did run
+
+
 def test_closed_loop_with_sqp_solves(torch_cuda):
     """the batched closed loop (robot_ocp_problem.py:184-260) with the full-SQP mode behind ocp_solver.solve(): a few
     SQP iterations per control step instead of one RTI iteration.  Status 2 (ACADOS_MAXITER) is not a failure for the loop

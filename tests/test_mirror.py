@@ -128,3 +128,23 @@ def test_long_horizon_mirror_matches_oracle(mirror, oracle):
     assert sel.sum() >= 2
     for k in ("u", "x"):
         assert _rel_rows(m[k], r[k])[sel].max() < 1e-6, k
+
+
+@pytest.mark.parametrize("glob,min_same", [(0, 0.95), (1, 0.85)])
+def test_sqp_mirror_matches_oracle(mirror, oracle, glob, min_same):
+    """the full-SQP instantiation of the warp kernel (outer loop, convergence test, merit line search inside the kernel) on the
+    CPU against the oracle's SQP loop: same statuses and SQP iteration counts up to the merit comparisons that rounding decides"""
+    B, lm, max_iter = 24, 0.05, 15
+    dims = world.MpcDims(20, 5, 2.0)
+    sc = world.random_scenarios(B, dims, seed=14, moving_start=True)
+    cfg = mirror.default_config(20, 5, 2.0, lm=lm, nlp_solver=1, nlp_iter_max=max_iter, nlp_globalization=glob)
+    m = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    out = mirror.solve_batch(cfg, sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"], m["x"], m["u"], m["sl"], m["su"], sqp=True)
+    r = {k: sc[k].copy() for k in ("x", "u", "sl", "su")}
+    ro = oracle.sqp_solve_batch(oracle.default_config(20, 5, 2.0, lm=lm), sc["x0"], sc["p"], sc["yref"], sc["zl"], sc["Zl"],
+                                r["x"], r["u"], r["sl"], r["su"], max_iter=max_iter, nthreads=4, globalization=glob)
+    assert np.mean(out["status"] == ro["status"]) >= min_same
+    assert np.mean(out["sqp_iter"] == ro["sqp_iter"]) >= min_same
+    same = (out["status"] == ro["status"]) & (out["sqp_iter"] == ro["sqp_iter"])
+    e = _rel_rows(m["u"], r["u"])
+    assert np.median(e[same]) < 1e-8
