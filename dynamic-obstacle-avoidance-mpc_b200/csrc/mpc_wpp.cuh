@@ -96,6 +96,13 @@ enum { PF_LAM = 0, PF_T, PF_TINV, PF_DD, PF_DT,              // per constraint; 
 #ifndef B2_WPP_FEEDBACK_GAIN
 #define B2_WPP_FEEDBACK_GAIN 0   // experiment: G = Lxu Luu^-1 formed once per factorisation, no triangular solve inside the sweeps
 #endif
+#ifndef B2_WPP_BOX_PIPE            // head(): next box slot's loads in flight while this one is processed
+#ifdef B2_WPP_ROLL_BOX
+#define B2_WPP_BOX_PIPE 0
+#else
+#define B2_WPP_BOX_PIPE B2_WPP_NO_DT
+#endif
+#endif
 #ifndef B2_WPP_FUSE_LIN
 #define B2_WPP_FUSE_LIN 1        // 0 never, 1 horizons > 32 nodes, 2 always: the linear-residual pass fused into the expansion pass
 #endif
@@ -254,6 +261,19 @@ struct WppSolver {
     {
         const double xv = Q<PF_XU>(s);
         lb = p.lb6[s] - xv; ub = p.ub6[s] - xv;          // [lbu, lbx] / [ubu, ubx] in slot order
+    }
+
+    // the nine private values of box slot s at this lane's node (head() has its own seven): requested one slot ahead of their
+    // use (B2_WPP_BOX_PIPE), in front of the `box_on` branch of the slot being processed
+    struct Box9 { double ll, lu, tl, tu, xu, dl, du, til, tiu; };
+    template <bool TINV_>
+    __device__ __forceinline__ Box9 box_load9(const int s_) const
+    {
+        Box9 r;
+        r.ll = Q<PF_LAM>(o_lb + s_); r.lu = Q<PF_LAM>(o_ub + s_); r.tl = Q<PF_T>(o_lb + s_); r.tu = Q<PF_T>(o_ub + s_);
+        r.xu = Q<PF_XU>(s_); r.dl = Q<PF_DD>(o_lb + s_); r.du = Q<PF_DD>(o_ub + s_);
+        r.til = TINV_ ? Q<PF_TINV>(o_lb + s_) : 0.0; r.tiu = TINV_ ? Q<PF_TINV>(o_ub + s_) : 0.0;
+        return r;
     }
 
     // ---- software prefetch of private rows (see B2_WPP_PF_LONG above) ---------------------------------------------
@@ -497,16 +517,41 @@ struct WppSolver {
 #pragma unroll
                 for (int i = 0; i < 5; i++) rg[2 + i] -= PP(i, k - 1);
             }
+#if B2_WPP_BOX_PIPE
+            // the private rows of box slot s+1 are requested before slot s is processed (its seven loads sit in front of the
+            // `box_on` branch of slot s): two slots share an L2 round trip instead of paying one each
+            struct BoxIn { double dl, ll, du, lu, xu, tl, tu; };
+            auto box_load = [&](const int s_) {
+                BoxIn r;
+                r.dl = Q<PF_DD>(o_lb + s_); r.ll = Q<PF_LAM>(o_lb + s_); r.du = Q<PF_DD>(o_ub + s_); r.lu = Q<PF_LAM>(o_ub + s_);
+                r.xu = Q<PF_XU>(s_); r.tl = Q<PF_T>(o_lb + s_); r.tu = Q<PF_T>(o_ub + s_);
+                return r;
+            };
+            BoxIn bnext = box_load(0);
+#endif
             B2_BOX_LOOP
             for (int s = 0; s < 6; s++) {
+#if B2_WPP_BOX_PIPE
+                const BoxIn bin = bnext;
+                if (s + 1 < 6) bnext = box_load(s + 1);
+#endif
                 if (!box_on(s, k)) continue;
                 const int il = o_lb + s, iu = o_ub + s;
+#if B2_WPP_BOX_PIPE
+                double ll = fma(a, bin.dl, bin.ll), lu_ = fma(a, bin.du, bin.lu);
+                const double lb = p.lb6[s] - bin.xu, ub = p.ub6[s] - bin.xu;
+#else
                 double ll = fma(a, Q<PF_DD>(il), Q<PF_LAM>(il)), lu_ = fma(a, Q<PF_DD>(iu), Q<PF_LAM>(iu));
                 double lb, ub;
                 box_bounds(s, lb, ub);
+#endif
                 double tl, tu;
                 if (B2_WPP_NO_DT) {
+#if B2_WPP_BOX_PIPE
+                    const double tlo = bin.tl, tuo = bin.tu;
+#else
                     const double tlo = Q<PF_T>(il), tuo = Q<PF_T>(iu);
+#endif
                     const double vos = S(o.cv + b2_slot2v(s), k), dvs = R<PF_DV>(b2_slot2v(s), k);
                     const double dtl = dvs + ((vos - lb) - tlo), dtu = -dvs + ((ub - vos) - tuo);      // = expand()'s dtl, dtu
                     tl = fma(a, dtl, tlo); tu = fma(a, dtu, tuo);
@@ -861,8 +906,22 @@ struct WppSolver {
                 double v[7];
 #pragma unroll
                 for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
+#if B2_WPP_BOX_PIPE
+                Box9 bnext = box_load9<true>(0);
+#endif
                 B2_BOX_LOOP
                 for (int s = 0; s < 6; s++) {
+#if B2_WPP_BOX_PIPE
+                    const Box9 bin = bnext;
+                    if (s + 1 < 6) bnext = box_load9<true>(s + 1);
+                    if (!box_on(s, k)) continue;
+                    const double ll = bin.ll, lu_ = bin.lu, tl = bin.tl, tu = bin.tu;
+                    const double lb = p.lb6[s] - bin.xu, ub = p.ub6[s] - bin.xu;
+                    const double vv = slot_get(v, s);
+                    const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
+                    const double ql = fma(ll, rdl, rm_of(kind, ll, tl, bin.dl, smu)) * bin.til;
+                    const double qu = fma(lu_, rdu, rm_of(kind, lu_, tu, bin.du, smu)) * bin.tiu;
+#else
                     if (!box_on(s, k)) continue;
                     const int il = o_lb + s, iu = o_ub + s;
                     const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
@@ -872,6 +931,7 @@ struct WppSolver {
                     const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
                     const double ql = fma(ll, rdl, rm_of(kind, ll, tl, Q<PF_DD>(il), smu)) * Q<PF_TINV>(il);
                     const double qu = fma(lu_, rdu, rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu)) * Q<PF_TINV>(iu);
+#endif
                     slot_add(gt, s, ql - qu);
                 }
                 // (the components that the obstacles do not touch leave the registers before their loop)
@@ -1084,31 +1144,46 @@ struct WppSolver {
             cv[i] = 0.0;
             if (MODE == XP_REFINE) cv[i] = S(o.cv + i, k);       // (dv, dpi already hold the corrected step: apply_correction())
         }
+#if B2_WPP_BOX_PIPE
+        Box9 bnext = box_load9<MODE != XP_LIN>(0);
+#endif
         B2_BOX_LOOP
         for (int s = 0; s < 6; s++) {
+#if B2_WPP_BOX_PIPE
+            const Box9 bin = bnext;
+            if (s + 1 < 6) bnext = box_load9<MODE != XP_LIN>(s + 1);
+#endif
             if (!box_on(s, k)) continue;
             const int il = o_lb + s, iu = o_ub + s;
+#if B2_WPP_BOX_PIPE
+            const double ll = bin.ll, lu_ = bin.lu, tl = bin.tl, tu = bin.tu;
+            const double lb = p.lb6[s] - bin.xu, ub = p.ub6[s] - bin.xu;
+            const double ddl_ = bin.dl, ddu_ = bin.du, til_ = bin.til, tiu_ = bin.tiu;
+#else
             const double ll = Q<PF_LAM>(il), lu_ = Q<PF_LAM>(iu), tl = Q<PF_T>(il), tu = Q<PF_T>(iu);
             double lb, ub;
             box_bounds(s, lb, ub);
+            const double ddl_ = Q<PF_DD>(il), ddu_ = Q<PF_DD>(iu);
+            const double til_ = MODE != XP_LIN ? Q<PF_TINV>(il) : 0.0, tiu_ = MODE != XP_LIN ? Q<PF_TINV>(iu) : 0.0;
+#endif
             const double vv = slot_get(v, s), dvv = slot_get(dv, s);
             const double rdl = (vv - lb) - tl, rdu = (ub - vv) - tu;
             const double dtl = dvv + rdl, dtu = -dvv + rdu;
             double dll, dlu;
             if (MODE == XP_SOLVE) {
-                dll = -fma(ll, dtl, rm_of(kind, ll, tl, Q<PF_DD>(il), smu)) * Q<PF_TINV>(il);
-                dlu = -fma(lu_, dtu, rm_of(kind, lu_, tu, Q<PF_DD>(iu), smu)) * Q<PF_TINV>(iu);
+                dll = -fma(ll, dtl, rm_of(kind, ll, tl, ddl_, smu)) * til_;
+                dlu = -fma(lu_, dtu, rm_of(kind, lu_, tu, ddu_, smu)) * tiu_;
                 Q<PF_DD>(il) = keep_dd ? dtl * dll : dll;
                 Q<PF_DD>(iu) = keep_dd ? dtu * dlu : dlu;
                 if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else if (MODE == XP_REFINE) {
                 const double cvv = slot_get(cv, s);
-                dll = fma(-(ll * cvv), Q<PF_TINV>(il), Q<PF_DD>(il));
-                dlu = fma(lu_ * cvv, Q<PF_TINV>(iu), Q<PF_DD>(iu));
+                dll = fma(-(ll * cvv), til_, ddl_);
+                dlu = fma(lu_ * cvv, tiu_, ddu_);
                 Q<PF_DD>(il) = dll; Q<PF_DD>(iu) = dlu;
                 if (!B2_WPP_NO_DT) { Q<PF_DT>(il) = dtl; Q<PF_DT>(iu) = dtu; }
             } else {
-                dll = Q<PF_DD>(il); dlu = Q<PF_DD>(iu);
+                dll = ddl_; dlu = ddu_;
             }
             consume<MODE>(il, ll, tl, dtl, dll, a, ap, ad, s1, s2);
             consume<MODE>(iu, lu_, tu, dtu, dlu, a, ap, ad, s1, s2);
