@@ -500,6 +500,19 @@ struct WppSolver {
             double v[7], rg[7], Hx[7], gt[7], hxy = 0.0;
             const double* Hd = k < N ? p.Hd : p.Hde;
             const double sc = scal(k);
+#if B2_WPP_BOX_PIPE
+            // the private rows of box slot s+1 are requested before slot s is processed (its seven loads sit in front of the
+            // `box_on` branch of slot s): two slots share an L2 round trip instead of paying one each
+            struct BoxIn { double dl, ll, du, lu, xu, tl, tu; };
+            auto box_load = [&](const int s_) {
+                BoxIn r;
+                r.dl = Q<PF_DD>(o_lb + s_); r.ll = Q<PF_LAM>(o_lb + s_); r.du = Q<PF_DD>(o_ub + s_); r.lu = Q<PF_LAM>(o_ub + s_);
+                r.xu = Q<PF_XU>(s_); r.tl = Q<PF_T>(o_lb + s_); r.tu = Q<PF_T>(o_ub + s_);
+                return r;
+            };
+            BoxIn bnext = box_load(0);                 // (with the node-level rows below: one round trip)
+#endif
+
 #pragma unroll
             for (int i = 0; i < 7; i++) { v[i] = VV(i, k); rg[i] = fma(Hd[i], v[i], Q<PF_G>(i)); Hx[i] = Hd[i] + p.reg_prim; gt[i] = 0.0; }
             double sv[10];
@@ -517,18 +530,6 @@ struct WppSolver {
 #pragma unroll
                 for (int i = 0; i < 5; i++) rg[2 + i] -= PP(i, k - 1);
             }
-#if B2_WPP_BOX_PIPE
-            // the private rows of box slot s+1 are requested before slot s is processed (its seven loads sit in front of the
-            // `box_on` branch of slot s): two slots share an L2 round trip instead of paying one each
-            struct BoxIn { double dl, ll, du, lu, xu, tl, tu; };
-            auto box_load = [&](const int s_) {
-                BoxIn r;
-                r.dl = Q<PF_DD>(o_lb + s_); r.ll = Q<PF_LAM>(o_lb + s_); r.du = Q<PF_DD>(o_ub + s_); r.lu = Q<PF_LAM>(o_ub + s_);
-                r.xu = Q<PF_XU>(s_); r.tl = Q<PF_T>(o_lb + s_); r.tu = Q<PF_T>(o_ub + s_);
-                return r;
-            };
-            BoxIn bnext = box_load(0);
-#endif
             B2_BOX_LOOP
             for (int s = 0; s < 6; s++) {
 #if B2_WPP_BOX_PIPE
@@ -904,11 +905,11 @@ struct WppSolver {
                 }
             } else {
                 double v[7];
-#pragma unroll
-                for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
 #if B2_WPP_BOX_PIPE
                 Box9 bnext = box_load9<true>(0);
 #endif
+#pragma unroll
+                for (int i = 0; i < 7; i++) { v[i] = VV(i, k); gt[i] = Q<PF_RG>(i); }
                 B2_BOX_LOOP
                 for (int s = 0; s < 6; s++) {
 #if B2_WPP_BOX_PIPE
